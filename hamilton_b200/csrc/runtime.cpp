@@ -1,0 +1,551 @@
+// runtime.cpp — C ABI implementation (include/hamilton_b200.h): system objects, NVRTC JIT of tape
+// systems, kernel dispatch, host<->device staging.  Host-only C++; the device code lives in
+// engine/hb_engine.cuh (hand-written) + the per-system derivative structs printed by sysgen.cpp.
+//
+// There is deliberately no CPU implementation of any compute entry point in this library.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nvrtc.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/hamilton_b200.h"
+#include "builtins.hpp"
+#include "sysgen.hpp"
+
+// ---- mirrors of the device-side declarations in engine/hb_engine.cuh (kept in sync by a static_assert in aot_kernels.cu)
+#define HB_MAXP 32
+struct HbKArgs {
+  const double* in; double* out; int* flags; const double* ts;
+  long long N; double dt; int nsteps; int layout; int s; int substeps;
+  unsigned long long seed; long long first;
+  double prm[HB_MAXP];
+};
+enum { K_STEP_RK4 = 0, K_STEP_RKF45, K_EVOLVE_RK4, K_EVOLVE_RKF45, K_HAM_EQS, K_TO_PHASE, K_FROM_PHASE, K_ENERGIES, K_UPOS, K_COUNT };
+static const char* const KERNEL_KINDS[K_COUNT] = {"step_rk4", "step_rkf45", "evolve_rk4", "evolve_rkf45", "ham_eqs",
+                                                  "to_phase", "from_phase", "energies", "upos"};
+#define HB_BLOCK 128
+
+// from aot_kernels.cu
+extern "C" const void* hb_aot_kernel(int builtin, int kernel_id);
+extern "C" const void* hb_aot_init_random(void);
+extern "C" size_t hb_aot_kargs_size(void);
+// from gen/engine_embed.inc (the engine header as a string, for NVRTC)
+extern const char hb_engine_src[];
+
+namespace {
+
+thread_local std::string g_err;
+hb_status fail(hb_status s, const std::string& msg) { g_err = msg; return s; }
+hb_status cuda_fail(cudaError_t e, const char* what) {
+  // errors that mean "this machine cannot run CUDA at all"
+  if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorInitializationError ||
+      e == cudaErrorNotSupported || e == cudaErrorSystemDriverMismatch || e == cudaErrorSystemNotReady)
+    return fail(HB_ERR_NO_DEVICE, std::string(what) + ": " + cudaGetErrorString(e) + " (no CUDA device; this library has no CPU fallback)");
+  return fail(HB_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(e_, #call); } while (0)
+
+hb_status need_device() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) { cudaGetLastError(); return cuda_fail(e, "cudaGetDeviceCount"); }
+  if (n <= 0) return fail(HB_ERR_NO_DEVICE, "no CUDA device; this library has no CPU fallback");
+  return HB_OK;
+}
+
+// ------------------------------------------------------------------------------ NVRTC -------
+struct Nvrtc {
+  void* h = nullptr;
+  decltype(&nvrtcCreateProgram) CreateProgram = nullptr;
+  decltype(&nvrtcCompileProgram) CompileProgram = nullptr;
+  decltype(&nvrtcGetCUBINSize) GetCUBINSize = nullptr;
+  decltype(&nvrtcGetCUBIN) GetCUBIN = nullptr;
+  decltype(&nvrtcGetProgramLogSize) GetProgramLogSize = nullptr;
+  decltype(&nvrtcGetProgramLog) GetProgramLog = nullptr;
+  decltype(&nvrtcDestroyProgram) DestroyProgram = nullptr;
+  decltype(&nvrtcGetErrorString) GetErrorString = nullptr;
+  std::string err;
+  bool load() {
+    if (h) return true;
+    const char* names[] = {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12", "libnvrtc.so.13"};
+    for (const char* n : names) { h = dlopen(n, RTLD_NOW | RTLD_LOCAL); if (h) break; }
+    if (!h) { err = "cannot dlopen libnvrtc (needed to compile tape systems)"; return false; }
+#define SYM(x) x = (decltype(x))dlsym(h, "nvrtc" #x); if (!x) { err = "libnvrtc lacks nvrtc" #x; return false; }
+    SYM(CreateProgram) SYM(CompileProgram) SYM(GetCUBINSize) SYM(GetCUBIN) SYM(GetProgramLogSize) SYM(GetProgramLog)
+    SYM(DestroyProgram) SYM(GetErrorString)
+#undef SYM
+    return true;
+  }
+};
+Nvrtc g_nvrtc;
+std::mutex g_nvrtc_mu;
+
+std::string jit_arch() {
+  if (const char* e = std::getenv("HB_JIT_ARCH")) return e;
+  int dev = 0;
+  cudaDeviceProp p;
+  if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&p, dev) == cudaSuccess) {
+    char buf[32];
+    const bool arch_specific = p.major >= 9;   // sm_90a / sm_100a / sm_103a
+    std::snprintf(buf, sizeof buf, "sm_%d%d%s", p.major, p.minor, arch_specific ? "a" : "");
+    return buf;
+  }
+  cudaGetLastError();
+  return "sm_100a";   // the target this library is written for
+}
+
+bool nvrtc_compile(const std::string& src, const std::string& arch, std::vector<char>& cubin, std::string& log) {
+  std::lock_guard<std::mutex> lk(g_nvrtc_mu);
+  if (!g_nvrtc.load()) { log = g_nvrtc.err; return false; }
+  nvrtcProgram prog;
+  const char* hdr_src[] = {hb_engine_src};
+  const char* hdr_name[] = {"hb_engine.cuh"};
+  nvrtcResult r = g_nvrtc.CreateProgram(&prog, src.c_str(), "hb_jit_system.cu", 1, hdr_src, hdr_name);
+  if (r != NVRTC_SUCCESS) { log = std::string("nvrtcCreateProgram: ") + g_nvrtc.GetErrorString(r); return false; }
+  std::string a = "--gpu-architecture=" + arch;
+  const char* opts[] = {a.c_str(), "--std=c++17", "-lineinfo", "--fmad=true", "-default-device"};
+  r = g_nvrtc.CompileProgram(prog, 5, opts);
+  size_t ls = 0;
+  g_nvrtc.GetProgramLogSize(prog, &ls);
+  if (ls > 1) { log.resize(ls); g_nvrtc.GetProgramLog(prog, &log[0]); }
+  if (r != NVRTC_SUCCESS) { log = std::string("nvrtcCompileProgram: ") + g_nvrtc.GetErrorString(r) + "\n" + log; g_nvrtc.DestroyProgram(&prog); return false; }
+  size_t cs = 0;
+  g_nvrtc.GetCUBINSize(prog, &cs);
+  cubin.resize(cs);
+  g_nvrtc.GetCUBIN(prog, cubin.data());
+  g_nvrtc.DestroyProgram(&prog);
+  return true;
+}
+
+}  // namespace
+
+// --------------------------------------------------------------------------- hb_system -------
+struct hb_system {
+  int m = 0, n = 0;
+  int builtin = -1;                    // hb_builtin id or -1 (tape / JIT)
+  std::vector<double> params;          // tape-level runtime parameters (<= HB_MAXP)
+  std::string source;                  // generated Sys struct
+  // JIT
+  std::vector<char> cubin;
+  cudaLibrary_t lib = nullptr;
+  const void* jit_kernels[K_COUNT] = {nullptr};
+  std::mutex mu;
+  bool loaded = false;
+
+  hb_status kernel(int kid, const void** fn) {
+    if (builtin >= 0) {
+      *fn = hb_aot_kernel(builtin, kid);
+      return *fn ? HB_OK : fail(HB_ERR_INVALID, "no such AOT kernel");
+    }
+    std::lock_guard<std::mutex> lk(mu);
+    if (!loaded) {
+      CU(cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+      for (int k = 0; k < K_COUNT; k++) {
+        cudaKernel_t kh;
+        std::string nm = std::string("hbk_") + KERNEL_KINDS[k];
+        CU(cudaLibraryGetKernel(&kh, lib, nm.c_str()));
+        jit_kernels[k] = (const void*)kh;
+      }
+      loaded = true;
+    }
+    *fn = jit_kernels[kid];
+    return HB_OK;
+  }
+};
+
+namespace {
+
+// Device scratch for HB_MEM_HOST calls: per-thread, grow-only, with a private stream.
+struct Scratch {
+  void* p[3] = {nullptr, nullptr, nullptr};
+  size_t cap[3] = {0, 0, 0};
+  cudaStream_t stream = nullptr;
+  int device = -1;
+  hb_status get(int slot, size_t bytes, void** out) {
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    if (dev != device) {   // device switched on this thread: drop the old buffers
+      for (int i = 0; i < 3; i++) { if (p[i]) { cudaSetDevice(device); cudaFree(p[i]); cudaSetDevice(dev); } p[i] = nullptr; cap[i] = 0; }
+      if (stream) { cudaStreamDestroy(stream); stream = nullptr; }
+      device = dev;
+    }
+    if (!stream) CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    if (bytes > cap[slot]) {
+      if (p[slot]) CU(cudaFree(p[slot]));
+      p[slot] = nullptr; cap[slot] = 0;
+      size_t want = bytes + bytes / 8 + 256;
+      CU(cudaMalloc(&p[slot], want));
+      cap[slot] = want;
+    }
+    *out = p[slot];
+    return HB_OK;
+  }
+};
+thread_local Scratch g_scratch;
+
+hb_status launch(const void* fn, const HbKArgs& a, long long work_items, cudaStream_t st) {
+  if (work_items <= 0) return HB_OK;
+  long long blocks = (work_items + HB_BLOCK - 1) / HB_BLOCK;
+  if (blocks > 0x7fffffffLL) blocks = 0x7fffffffLL;
+  void* args[] = {(void*)&a};
+  CU(cudaLaunchKernel(fn, dim3((unsigned)blocks), dim3(HB_BLOCK), args, 0, st));
+  return HB_OK;
+}
+
+void fill_params(const hb_system* s, HbKArgs& a) {
+  std::memset(&a, 0, sizeof a);
+  for (size_t k = 0; k < s->params.size() && k < HB_MAXP; k++) a.prm[k] = s->params[k];
+}
+
+// Generic batch runner.  in_d / out_d = doubles per trajectory on each side; `out_batches` output
+// batches are stored back to back (evolve).  `ts` (host, s doubles) is uploaded when non-null.
+hb_status run_batch(const hb_system* sys, int kid, HbKArgs a, int64_t N, hb_memspace mem, const double* in, int in_d,
+                    double* out, int out_d, int out_batches, int32_t* flags, const double* ts, int s, void* stream) {
+  if (!sys) return fail(HB_ERR_INVALID, "null system");
+  if (N < 0) return fail(HB_ERR_INVALID, "negative batch size");
+  if (N == 0) return HB_OK;
+  if (!in || !out) return fail(HB_ERR_INVALID, "null batch pointer");
+  hb_status rc = need_device();
+  if (rc) return rc;
+  const void* fn = nullptr;
+  rc = const_cast<hb_system*>(sys)->kernel(kid, &fn);
+  if (rc) return rc;
+  a.N = N;
+  const size_t in_bytes = (size_t)N * in_d * sizeof(double), out_bytes = (size_t)N * out_d * out_batches * sizeof(double);
+  if (mem == HB_MEM_DEVICE) {
+    cudaStream_t st = (cudaStream_t)stream;
+    a.in = in; a.out = out; a.flags = flags;
+    double* dts = nullptr;
+    if (ts) {
+      CU(cudaMallocAsync((void**)&dts, sizeof(double) * s, st));
+      CU(cudaMemcpyAsync(dts, ts, sizeof(double) * s, cudaMemcpyHostToDevice, st));   // ts is tiny; pageable copy is staged by the driver
+      a.ts = dts;
+    }
+    rc = launch(fn, a, N, st);
+    if (dts) cudaFreeAsync(dts, st);
+    return rc;
+  }
+  // HB_MEM_HOST: stage through per-thread device scratch on a private stream and wait.
+  void *din = nullptr, *dout = nullptr, *dfl = nullptr;
+  const bool inplace = (const void*)in == (const void*)out && in_bytes == out_bytes;
+  if ((rc = g_scratch.get(0, in_bytes + (ts ? sizeof(double) * s : 0), &din))) return rc;
+  if (inplace) dout = din; else if ((rc = g_scratch.get(1, out_bytes, &dout))) return rc;
+  cudaStream_t st = g_scratch.stream;
+  CU(cudaMemcpyAsync(din, in, in_bytes, cudaMemcpyHostToDevice, st));
+  if (ts) {
+    double* dts = (double*)((char*)din + in_bytes);
+    CU(cudaMemcpyAsync(dts, ts, sizeof(double) * s, cudaMemcpyHostToDevice, st));
+    a.ts = dts;
+  }
+  if (flags) {
+    if ((rc = g_scratch.get(2, sizeof(int32_t) * N, &dfl))) return rc;
+    CU(cudaMemcpyAsync(dfl, flags, sizeof(int32_t) * N, cudaMemcpyHostToDevice, st));
+  }
+  a.in = (const double*)din; a.out = (double*)dout; a.flags = (int*)dfl;
+  if ((rc = launch(fn, a, N, st))) return rc;
+  CU(cudaMemcpyAsync(out, dout, out_bytes, cudaMemcpyDeviceToHost, st));
+  if (flags) CU(cudaMemcpyAsync(flags, dfl, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return HB_OK;
+}
+
+bool bad_layout(hb_layout l) { return l != HB_LAYOUT_AOS && l != HB_LAYOUT_SOA; }
+
+}  // namespace
+
+// ================================================================================ C ABI ======
+extern "C" {
+
+int32_t hb_abi_version(void) { return HB_ABI_VERSION; }
+const char* hb_last_error(void) { return g_err.c_str(); }
+
+hb_status hb_device_count(int32_t* count) {
+  if (!count) return fail(HB_ERR_INVALID, "null count");
+  *count = 0;
+  hb_status rc = need_device();
+  if (rc) return rc;
+  int n = 0;
+  CU(cudaGetDeviceCount(&n));
+  *count = n;
+  return HB_OK;
+}
+hb_status hb_set_device(int32_t device) {
+  hb_status rc = need_device();
+  if (rc) return rc;
+  CU(cudaSetDevice(device));
+  return HB_OK;
+}
+
+hb_status hb_system_builtin(hb_builtin id, const double* params, int32_t n_params, hb_system** out) {
+  if (!out) return fail(HB_ERR_INVALID, "null out");
+  *out = nullptr;
+  if ((int)id < 0 || (int)id >= HB_SYS__COUNT) return fail(HB_ERR_INVALID, "unknown builtin system id");
+  if (n_params < 0 || (n_params > 0 && !params)) return fail(HB_ERR_INVALID, "bad params");
+  hb::SystemSpec spec;
+  if (!hb::builtin_spec(id, spec)) return fail(HB_ERR_INVALID, "no such builtin");
+  hb_system* s = new hb_system();
+  s->m = spec.m; s->n = spec.n; s->builtin = (int)id;
+  hb::builtin_params(id, params, n_params, s->params);
+  hb::GeneratedSystem g;
+  std::string err;
+  if (hb::generate_system(spec, std::string("HbSys_") + hb::builtin_name(id), g, err)) s->source = g.source;
+  *out = s;
+  return HB_OK;
+}
+
+hb_status hb_system_from_tape(int32_t m, int32_t n, const double* inertia, const hb_tape* f, const hb_tape* u,
+                              int32_t u_on_cartesian, const double* params, int32_t n_params, hb_system** out) {
+  if (!out) return fail(HB_ERR_INVALID, "null out");
+  *out = nullptr;
+  if (!inertia || !f || !u) return fail(HB_ERR_INVALID, "null argument");
+  if (n < 1 || n > HB_MAX_N || m < 1 || m > HB_MAX_M) return fail(HB_ERR_INVALID, "dimensions out of range (1 <= n <= 16, 1 <= m <= 48)");
+  if (n_params < 0 || n_params > HB_MAXP || (n_params > 0 && !params)) return fail(HB_ERR_INVALID, "bad params (at most 32)");
+  if (f->n_in != n || f->n_out != m || !f->ops || !f->outs || f->n_ops < 1) return fail(HB_ERR_TAPE, "f tape must map n inputs to m outputs");
+  if (u->n_in != (u_on_cartesian ? m : n) || u->n_out != 1 || !u->ops || !u->outs || u->n_ops < 1)
+    return fail(HB_ERR_TAPE, "u tape must map n (or m when u_on_cartesian) inputs to 1 output");
+  hb::SystemSpec spec;
+  spec.m = m; spec.n = n; spec.n_params = n_params; spec.u_on_cartesian = u_on_cartesian != 0;
+  for (int i = 0; i < m; i++) { hb::InertiaTerm t; t.value = inertia[i]; spec.inertia.push_back(t); }
+  spec.f_ops.assign(f->ops, f->ops + f->n_ops);
+  spec.f_outs.assign(f->outs, f->outs + m);
+  spec.u_ops.assign(u->ops, u->ops + u->n_ops);
+  spec.u_out = u->outs[0];
+  hb::GeneratedSystem g;
+  std::string err;
+  if (!hb::generate_system(spec, "HbSysJit", g, err)) return fail(HB_ERR_TAPE, err);
+  std::string tu = hb::jit_translation_unit(g, "hbk");
+  std::vector<char> cubin;
+  std::string log;
+  if (!nvrtc_compile(tu, jit_arch(), cubin, log)) return fail(HB_ERR_COMPILE, log);
+  hb_system* s = new hb_system();
+  s->m = m; s->n = n; s->builtin = -1;
+  s->params.assign(params, params + n_params);
+  s->source = g.source;
+  s->cubin.swap(cubin);
+  *out = s;
+  return HB_OK;
+}
+
+void hb_system_free(hb_system* sys) {
+  if (!sys) return;
+  if (sys->lib) cudaLibraryUnload(sys->lib);
+  delete sys;
+}
+hb_status hb_system_dims(const hb_system* sys, int32_t* m, int32_t* n) {
+  if (!sys) return fail(HB_ERR_INVALID, "null system");
+  if (m) *m = sys->m;
+  if (n) *n = sys->n;
+  return HB_OK;
+}
+size_t hb_system_source(const hb_system* sys, char* buf, size_t cap) {
+  if (!sys) return 0;
+  size_t need = sys->source.size() + 1;
+  if (buf && cap) { size_t k = need < cap ? need : cap; std::memcpy(buf, sys->source.c_str(), k - 1); buf[k - 1] = 0; }
+  return need;
+}
+
+hb_status hb_batch_ham_eqs(const hb_system* sys, int64_t N, hb_layout layout, hb_memspace mem, const double* y, double* dy,
+                           int32_t* flags, void* stream) {
+  if (!sys) return fail(HB_ERR_INVALID, "null system");
+  if (bad_layout(layout)) return fail(HB_ERR_INVALID, "bad layout");
+  HbKArgs a; fill_params(sys, a); a.layout = layout;
+  return run_batch(sys, K_HAM_EQS, a, N, mem, y, 2 * sys->n, dy, 2 * sys->n, 1, flags, nullptr, 0, stream);
+}
+
+hb_status hb_batch_step(const hb_system* sys, hb_integrator integ, double dt, int32_t nsteps, int64_t N, hb_layout layout,
+                        hb_memspace mem, const double* y_in, double* y_out, int32_t* flags, void* stream) {
+  if (!sys) return fail(HB_ERR_INVALID, "null system");
+  if (bad_layout(layout)) return fail(HB_ERR_INVALID, "bad layout");
+  if (integ != HB_INTEG_RK4 && integ != HB_INTEG_RKF45_GSL) return fail(HB_ERR_INVALID, "unknown integrator");
+  if (nsteps < 0) return fail(HB_ERR_INVALID, "negative nsteps");
+  if (integ == HB_INTEG_RKF45_GSL && !(dt > 0.0)) return fail(HB_ERR_INVALID, "RKF45_GSL needs dt > 0");
+  HbKArgs a; fill_params(sys, a); a.layout = layout; a.dt = dt; a.nsteps = nsteps;
+  return run_batch(sys, integ == HB_INTEG_RK4 ? K_STEP_RK4 : K_STEP_RKF45, a, N, mem, y_in, 2 * sys->n, y_out, 2 * sys->n, 1, flags,
+                   nullptr, 0, stream);
+}
+
+hb_status hb_batch_evolve(const hb_system* sys, hb_integrator integ, int32_t rk4_substeps, int64_t N, hb_layout layout,
+                          hb_memspace mem, const double* y0, const double* ts, int32_t s, double* out, int32_t* flags, void* stream) {
+  if (!sys) return fail(HB_ERR_INVALID, "null system");
+  if (bad_layout(layout)) return fail(HB_ERR_INVALID, "bad layout");
+  if (integ != HB_INTEG_RK4 && integ != HB_INTEG_RKF45_GSL) return fail(HB_ERR_INVALID, "unknown integrator");
+  if (!ts || s < 2) return fail(HB_ERR_INVALID, "evolveHam needs at least two grid times (2 <= s, src/Numeric/Hamilton.hs:435)");
+  for (int k = 1; k < s; k++) if (!(ts[k] >= ts[k - 1])) return fail(HB_ERR_INVALID, "time grid must be non-decreasing");
+  if (integ == HB_INTEG_RK4 && rk4_substeps < 1) return fail(HB_ERR_INVALID, "rk4_substeps must be >= 1");
+  HbKArgs a; fill_params(sys, a); a.layout = layout; a.s = s; a.substeps = rk4_substeps;
+  return run_batch(sys, integ == HB_INTEG_RK4 ? K_EVOLVE_RK4 : K_EVOLVE_RKF45, a, N, mem, y0, 2 * sys->n, out, 2 * sys->n, s, flags, ts,
+                   s, stream);
+}
+
+hb_status hb_batch_to_phase(const hb_system* sys, int64_t N, hb_layout layout, hb_memspace mem, const double* c, double* y, void* stream) {
+  if (!sys) return fail(HB_ERR_INVALID, "null system");
+  if (bad_layout(layout)) return fail(HB_ERR_INVALID, "bad layout");
+  HbKArgs a; fill_params(sys, a); a.layout = layout;
+  return run_batch(sys, K_TO_PHASE, a, N, mem, c, 2 * sys->n, y, 2 * sys->n, 1, nullptr, nullptr, 0, stream);
+}
+hb_status hb_batch_from_phase(const hb_system* sys, int64_t N, hb_layout layout, hb_memspace mem, const double* y, double* c,
+                              int32_t* flags, void* stream) {
+  if (!sys) return fail(HB_ERR_INVALID, "null system");
+  if (bad_layout(layout)) return fail(HB_ERR_INVALID, "bad layout");
+  HbKArgs a; fill_params(sys, a); a.layout = layout;
+  return run_batch(sys, K_FROM_PHASE, a, N, mem, y, 2 * sys->n, c, 2 * sys->n, 1, flags, nullptr, 0, stream);
+}
+hb_status hb_batch_energies(const hb_system* sys, int64_t N, hb_layout layout, hb_memspace mem, const double* y, double* out4,
+                            int32_t* flags, void* stream) {
+  if (!sys) return fail(HB_ERR_INVALID, "null system");
+  if (bad_layout(layout)) return fail(HB_ERR_INVALID, "bad layout");
+  HbKArgs a; fill_params(sys, a); a.layout = layout;
+  return run_batch(sys, K_ENERGIES, a, N, mem, y, 2 * sys->n, out4, 4, 1, flags, nullptr, 0, stream);
+}
+hb_status hb_batch_underlying_pos(const hb_system* sys, int64_t N, hb_layout layout, hb_memspace mem, const double* q, double* x,
+                                  void* stream) {
+  if (!sys) return fail(HB_ERR_INVALID, "null system");
+  if (bad_layout(layout)) return fail(HB_ERR_INVALID, "bad layout");
+  HbKArgs a; fill_params(sys, a); a.layout = layout;
+  return run_batch(sys, K_UPOS, a, N, mem, q, sys->n, x, sys->m, 1, nullptr, nullptr, 0, stream);
+}
+
+hb_status hb_batch_init_random(const hb_system* sys, uint64_t seed, int64_t first, int64_t N, hb_layout layout, const double* lo,
+                               const double* hi, double* y_device, void* stream) {
+  if (!sys || !lo || !hi || !y_device) return fail(HB_ERR_INVALID, "null argument");
+  if (bad_layout(layout) || N < 0 || first < 0) return fail(HB_ERR_INVALID, "bad argument");
+  const int D = 2 * sys->n;
+  if (2 * D > HB_MAXP) return fail(HB_ERR_INVALID, "too many components");
+  hb_status rc = need_device();
+  if (rc) return rc;
+  HbKArgs a; std::memset(&a, 0, sizeof a);
+  a.out = y_device; a.N = N; a.nsteps = D; a.layout = layout; a.seed = seed; a.first = first;
+  for (int c = 0; c < D; c++) { a.prm[c] = lo[c]; a.prm[D + c] = hi[c]; }
+  return launch(hb_aot_init_random(), a, N * D, (cudaStream_t)stream);
+}
+
+// ---- single-trajectory mirrors ---------------------------------------------------------------
+static hb_status one_flag(hb_status rc, int32_t flag) {
+  if (rc) return rc;
+  if (flag) {
+    std::string m = "numerical failure:";
+    if (flag & HB_FLAG_NOT_SPD) m += " mass matrix JtWJ not positive definite (reference: `inv` fails)";
+    if (flag & HB_FLAG_NONFINITE) m += " non-finite state";
+    if (flag & HB_FLAG_STEP_FAILED) m += " RKF45 step-size control failed";
+    return fail(HB_ERR_NUMERIC, m);
+  }
+  return HB_OK;
+}
+#define NEED(sys, ...) do { if (!(sys)) return fail(HB_ERR_INVALID, "null system"); const void* ps_[] = {__VA_ARGS__}; \
+  for (const void* p_ : ps_) if (!p_) return fail(HB_ERR_INVALID, "null pointer"); } while (0)
+
+static void pack(const hb_system* s, const double* a, const double* b, double* y) {
+  std::memcpy(y, a, sizeof(double) * s->n); std::memcpy(y + s->n, b, sizeof(double) * s->n);
+}
+
+hb_status hb_underlying_pos(const hb_system* sys, const double* q, double* x) {
+  NEED(sys, q, x);
+  return hb_batch_underlying_pos(sys, 1, HB_LAYOUT_AOS, HB_MEM_HOST, q, x, nullptr);
+}
+hb_status hb_pe(const hb_system* sys, const double* q, double* u) {
+  NEED(sys, q, u);
+  double y[2 * HB_MAX_N] = {0}, o[4]; int32_t fl = 0;
+  std::memcpy(y, q, sizeof(double) * sys->n);   // p = 0: U does not depend on it
+  hb_status rc = hb_batch_energies(sys, 1, HB_LAYOUT_AOS, HB_MEM_HOST, y, o, nullptr, nullptr);
+  (void)fl;
+  if (rc) return rc;
+  *u = o[1];
+  return HB_OK;
+}
+hb_status hb_momenta(const hb_system* sys, const double* q, const double* v, double* p) {
+  NEED(sys, q, v, p);
+  double c[2 * HB_MAX_N], y[2 * HB_MAX_N];
+  pack(sys, q, v, c);
+  hb_status rc = hb_batch_to_phase(sys, 1, HB_LAYOUT_AOS, HB_MEM_HOST, c, y, nullptr);
+  if (rc) return rc;
+  std::memcpy(p, y + sys->n, sizeof(double) * sys->n);
+  return HB_OK;
+}
+hb_status hb_velocities(const hb_system* sys, const double* q, const double* p, double* v) {
+  NEED(sys, q, p, v);
+  double c[2 * HB_MAX_N], y[2 * HB_MAX_N]; int32_t fl = 0;
+  pack(sys, q, p, y);
+  hb_status rc = one_flag(hb_batch_from_phase(sys, 1, HB_LAYOUT_AOS, HB_MEM_HOST, y, c, &fl, nullptr), fl);
+  if (rc) return rc;
+  std::memcpy(v, c + sys->n, sizeof(double) * sys->n);
+  return HB_OK;
+}
+static hb_status energies_p(const hb_system* sys, const double* q, const double* p, double* o4) {
+  double y[2 * HB_MAX_N]; int32_t fl = 0;
+  pack(sys, q, p, y);
+  return one_flag(hb_batch_energies(sys, 1, HB_LAYOUT_AOS, HB_MEM_HOST, y, o4, &fl, nullptr), fl);
+}
+static hb_status energies_c(const hb_system* sys, const double* q, const double* v, double* o4) {
+  double p[HB_MAX_N];
+  hb_status rc = hb_momenta(sys, q, v, p);   // keC = (v . momenta) / 2 = keP at toPhase(c)
+  if (rc) return rc;
+  return energies_p(sys, q, p, o4);
+}
+hb_status hb_ke_p(const hb_system* sys, const double* q, const double* p, double* t) {
+  NEED(sys, q, p, t); double o[4]; hb_status rc = energies_p(sys, q, p, o); if (!rc) *t = o[0]; return rc;
+}
+hb_status hb_hamiltonian(const hb_system* sys, const double* q, const double* p, double* h) {
+  NEED(sys, q, p, h); double o[4]; hb_status rc = energies_p(sys, q, p, o); if (!rc) *h = o[2]; return rc;
+}
+hb_status hb_ke_c(const hb_system* sys, const double* q, const double* v, double* t) {
+  NEED(sys, q, v, t); double o[4]; hb_status rc = energies_c(sys, q, v, o); if (!rc) *t = o[0]; return rc;
+}
+hb_status hb_lagrangian(const hb_system* sys, const double* q, const double* v, double* l) {
+  NEED(sys, q, v, l); double o[4]; hb_status rc = energies_c(sys, q, v, o); if (!rc) *l = o[3]; return rc;
+}
+hb_status hb_ham_eqs(const hb_system* sys, const double* q, const double* p, double* dq, double* dp) {
+  NEED(sys, q, p, dq, dp);
+  double y[2 * HB_MAX_N], dy[2 * HB_MAX_N]; int32_t fl = 0;
+  pack(sys, q, p, y);
+  hb_status rc = one_flag(hb_batch_ham_eqs(sys, 1, HB_LAYOUT_AOS, HB_MEM_HOST, y, dy, &fl, nullptr), fl);
+  if (rc) return rc;
+  std::memcpy(dq, dy, sizeof(double) * sys->n); std::memcpy(dp, dy + sys->n, sizeof(double) * sys->n);
+  return HB_OK;
+}
+hb_status hb_step_ham(const hb_system* sys, double r, const double* q, const double* p, double* q_out, double* p_out) {
+  NEED(sys, q, p, q_out, p_out);
+  double y[2 * HB_MAX_N], yo[2 * HB_MAX_N]; int32_t fl = 0;
+  pack(sys, q, p, y);
+  hb_status rc = one_flag(hb_batch_step(sys, HB_INTEG_RKF45_GSL, r, 1, 1, HB_LAYOUT_AOS, HB_MEM_HOST, y, yo, &fl, nullptr), fl);
+  if (rc) return rc;
+  std::memcpy(q_out, yo, sizeof(double) * sys->n); std::memcpy(p_out, yo + sys->n, sizeof(double) * sys->n);
+  return HB_OK;
+}
+hb_status hb_evolve_ham(const hb_system* sys, const double* q0, const double* p0, const double* ts, int32_t s, double* out) {
+  NEED(sys, q0, p0, ts, out);
+  double y[2 * HB_MAX_N]; int32_t fl = 0;
+  pack(sys, q0, p0, y);
+  return one_flag(hb_batch_evolve(sys, HB_INTEG_RKF45_GSL, 1, 1, HB_LAYOUT_AOS, HB_MEM_HOST, y, ts, s, out, &fl, nullptr), fl);
+}
+hb_status hb_step_ham_c(const hb_system* sys, double r, const double* q, const double* v, double* q_out, double* v_out) {
+  NEED(sys, q, v, q_out, v_out);
+  double p[HB_MAX_N], qo[HB_MAX_N], po[HB_MAX_N];
+  hb_status rc = hb_momenta(sys, q, v, p);                  // toPhase
+  if (!rc) rc = hb_step_ham(sys, r, q, p, qo, po);          // stepHam
+  if (!rc) rc = hb_velocities(sys, qo, po, v_out);          // fromPhase
+  if (!rc) std::memcpy(q_out, qo, sizeof(double) * sys->n);
+  return rc;
+}
+hb_status hb_evolve_ham_c(const hb_system* sys, const double* q0, const double* v0, const double* ts, int32_t s, double* out) {
+  NEED(sys, q0, v0, ts, out);
+  if (s < 2) return fail(HB_ERR_INVALID, "evolveHamC needs at least two grid times");
+  double p[HB_MAX_N];
+  hb_status rc = hb_momenta(sys, q0, v0, p);
+  if (rc) return rc;
+  std::vector<double> ph((size_t)s * 2 * sys->n);
+  if ((rc = hb_evolve_ham(sys, q0, p, ts, s, ph.data()))) return rc;
+  std::vector<int32_t> fl((size_t)s, 0);
+  rc = hb_batch_from_phase(sys, s, HB_LAYOUT_AOS, HB_MEM_HOST, ph.data(), out, fl.data(), nullptr);   // fmap (fromPhase s)
+  if (rc) return rc;
+  int32_t any = 0; for (int32_t f : fl) any |= f;
+  return one_flag(HB_OK, any);
+}
+
+}  // extern "C"

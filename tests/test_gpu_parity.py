@@ -1,0 +1,207 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Tolerance: |dq|, |dp| < 1e-10 per step (BASELINE.json north_star), applied as abs/(1+|ref|)."""
+import numpy as np
+import pytest
+
+import hamilton_b200 as hb
+from hamilton_b200 import _lib as L
+from tests.common import BOXES, SEED, maxerr, random_phases, tape_args
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+NAMES = list(BOXES)
+SMALL = [n for n in NAMES if n != "chain12"]
+
+
+def systems_for(name, O):
+    sid = BOXES[name][0]
+    aot = hb.systems.builtin(sid)
+    return aot, O.OracleSystem.builtin(sid)
+
+
+@pytest.fixture(scope="module")
+def jit_cache():
+    return {}
+
+
+def jit_system(name, cache):
+    if name not in cache:
+        cache[name] = hb.systems.from_def(hb.systems.DEFS[BOXES[name][0]]())
+    return cache[name]
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_ham_eqs_aot_vs_oracle(name, oracle_mod):
+    g, o = systems_for(name, oracle_mod)
+    y = random_phases(name, 257)
+    assert maxerr(g.batch_ham_eqs(y), o.batch_ham_eqs(y)) < TOL
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_ham_eqs_jit_vs_oracle_tape(name, oracle_mod, jit_cache):
+    """Tape systems: NVRTC-compiled product vs the oracle's tape interpreter AND its native fixture."""
+    g = jit_system(name, jit_cache)
+    m, n, w, fo, fouts, uo, uout, cart = tape_args(g)
+    ot = oracle_mod.OracleSystem.from_tape(m, n, w, fo, fouts, uo, uout, cart)
+    on = oracle_mod.OracleSystem.builtin(BOXES[name][0])
+    y = random_phases(name, 129)
+    dg = g.batch_ham_eqs(y)
+    assert maxerr(dg, ot.batch_ham_eqs(y)) < TOL
+    assert maxerr(dg, on.batch_ham_eqs(y)) < TOL
+
+
+@pytest.mark.parametrize("name", NAMES)
+@pytest.mark.parametrize("nsteps", [1, 10])
+def test_rk4_step_vs_oracle(name, nsteps, oracle_mod):
+    g, o = systems_for(name, oracle_mod)
+    y = random_phases(name, 64 if name == "chain12" else 300)
+    yo, bad = o.batch_step(y, 0, 0.01, nsteps)
+    assert bad == 0
+    fl = np.zeros(len(y), np.int32)
+    yg = g.batch_step(y, 0.01, nsteps, integ=L.RK4, flags=fl)
+    assert not fl.any()
+    assert maxerr(yg, yo) < TOL * nsteps
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_step_ham_rkf45_vs_oracle(name, oracle_mod):
+    """Reference semantics: one `stepHam 0.01` = fresh GSL-RKF45 solve over (0, 0.01)."""
+    g, o = systems_for(name, oracle_mod)
+    y = random_phases(name, 32 if name == "chain12" else 200)
+    yo, bad = o.batch_step(y, 1, 0.01, 1)
+    assert bad == 0
+    yg = g.batch_step(y, 0.01, 1, integ=L.RKF45_GSL)
+    assert maxerr(yg, yo) < TOL
+
+
+@pytest.mark.parametrize("name", ["double_pendulum", "two_body", "room"])
+def test_step_ham_demo_rate_with_rejections(name, oracle_mod):
+    """dt = 1/12 (the demo's frame step, app/Examples.hs:415,429) makes the controller reject steps."""
+    g, o = systems_for(name, oracle_mod)
+    y = random_phases(name, 100)
+    yo, bad = o.batch_step(y, 1, 1.0 / 12, 3)
+    yg = g.batch_step(y, 1.0 / 12, 3, integ=L.RKF45_GSL)
+    assert bad == 0
+    assert maxerr(yg, yo) < 1e-9   # 3 chained adaptive solves; step sequences identical, rounding differs
+
+
+@pytest.mark.parametrize("layout", [L.AOS, L.SOA])
+@pytest.mark.parametrize("mem", ["host", "device"])
+def test_layouts_and_memspaces(layout, mem, oracle_mod):
+    import torch
+    g, o = systems_for("double_pendulum", oracle_mod)
+    y = random_phases("double_pendulum", 1000)
+    yo, _ = o.batch_step(y, 0, 0.01, 2)
+    yin = np.ascontiguousarray(y.T) if layout == L.SOA else y
+    if mem == "device":
+        t = torch.from_numpy(yin).cuda()
+        out = g.batch_step(t, 0.01, 2, layout=layout)
+        torch.cuda.synchronize()
+        out = out.cpu().numpy()
+    else:
+        out = g.batch_step(yin, 0.01, 2, layout=layout)
+    if layout == L.SOA:
+        out = out.T
+    assert maxerr(out, yo) < TOL
+
+
+def test_config1_anchor_teacher_forced(oracle_mod):
+    """BASELINE config 1: double pendulum, Cfg (pi/2, 0) (0, 0), 1000 x stepHam 0.01, compared every step
+    from the oracle's state (teacher forcing), for both integrators."""
+    g, o = systems_for("double_pendulum", oracle_mod)
+    q, p = np.array([np.pi / 2, 0.0]), o.momenta([np.pi / 2, 0.0], [0.0, 0.0])
+    states = [np.r_[q, p]]
+    for _ in range(1000):
+        q, p = o.step_ham(0.01, q, p)
+        states.append(np.r_[q, p])
+    S = np.array(states)
+    got = g.batch_step(S[:-1].copy(), 0.01, 1, integ=L.RKF45_GSL)
+    assert np.max(np.abs(got - S[1:])) < TOL
+    rk4_o, _ = o.batch_step(S[:-1].copy(), 0, 0.01, 1)
+    rk4_g = g.batch_step(S[:-1].copy(), 0.01, 1, integ=L.RK4)
+    assert np.max(np.abs(rk4_g - rk4_o)) < TOL
+
+
+@pytest.mark.parametrize("name", ["double_pendulum", "two_body", "spring"])
+def test_evolve_grid_vs_oracle(name, oracle_mod):
+    g, o = systems_for(name, oracle_mod)
+    y = random_phases(name, 16)
+    ts = np.linspace(0.0, 1.0, 11)
+    got = g.batch_evolve(y, ts, integ=L.RKF45_GSL)     # (s, N, 2n)
+    n = o.n
+    for i in range(len(y)):
+        ref = o.evolve_ham(y[i, :n], y[i, n:], ts)
+        assert maxerr(got[:, i, :], ref) < 1e-9
+    assert np.array_equal(got[0], y)                    # first row is the initial state
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_config_phase_maps_and_energies(name, oracle_mod):
+    g, o = systems_for(name, oracle_mod)
+    y = random_phases(name, 50)
+    n = o.n
+    c = g.batch_from_phase(y)
+    vo = np.array([o.velocities(r[:n], r[n:]) for r in y])
+    assert maxerr(c[:, n:], vo) < TOL
+    back = g.batch_to_phase(c)
+    assert maxerr(back, y) < 1e-9                       # fromPhase . toPhase = id
+    po = np.array([o.momenta(r[:n], r[n:]) for r in c])
+    assert maxerr(back[:, n:], po) < 1e-9
+    e = g.batch_energies(y)
+    eo = np.array([[o.keP(r[:n], r[n:]), o.pe(r[:n]), o.hamiltonian(r[:n], r[n:]), 0.0] for r in y])
+    assert maxerr(e[:, :3], eo[:, :3]) < TOL
+    assert maxerr(e[:, 3], eo[:, 0] - eo[:, 1]) < TOL
+    x = g.batch_underlying_pos(np.ascontiguousarray(y[:, :n]))
+    xo = np.array([o.underlying_pos(r[:n]) for r in y])
+    assert maxerr(x, xo) < TOL
+
+
+def test_single_trajectory_api_matches_oracle(oracle_mod):
+    """The Haskell-shaped calls (README.md:124-165 usage) on one Phase."""
+    s = hb.systems.builtin(hb.systems.DOUBLE_PENDULUM, [1.0, 2.0])
+    o = oracle_mod.OracleSystem.builtin(1, [1.0, 2.0])
+    c0 = hb.Cfg([1.0, 0.0], [0.0, 0.5])
+    ph = hb.toPhase(s, c0)
+    assert maxerr(ph.phsMomenta, o.momenta(c0.cfgPositions, c0.cfgVelocities)) < TOL
+    assert abs(hb.keC(s, c0) - o.keC(c0.cfgPositions, c0.cfgVelocities)) < TOL
+    assert abs(hb.lagrangian(s, c0) - o.lagrangian(c0.cfgPositions, c0.cfgVelocities)) < TOL
+    assert abs(hb.hamiltonian(s, ph) - o.hamiltonian(ph.phsPositions, ph.phsMomenta)) < TOL
+    assert abs(hb.pe(s, ph.phsPositions) - o.pe(ph.phsPositions)) < TOL
+    dq, dp = hb.hamEqs(s, ph)
+    dqo, dpo = o.ham_eqs(ph.phsPositions, ph.phsMomenta)
+    assert maxerr(dq, dqo) < TOL and maxerr(dp, dpo) < TOL
+    p1 = hb.stepHam(0.1, s, ph)
+    qo, po = o.step_ham(0.1, ph.phsPositions, ph.phsMomenta)
+    assert maxerr(np.r_[p1.phsPositions, p1.phsMomenta], np.r_[qo, po]) < TOL
+    ts = np.arange(0, 1.05, 0.1)
+    ev = hb.evolveHam(s, ph, ts)
+    ref = o.evolve_ham(ph.phsPositions, ph.phsMomenta, ts)
+    assert maxerr(np.array([np.r_[e.phsPositions, e.phsMomenta] for e in ev]), ref) < 1e-9
+    assert hb.evolveHam_(s, ph, []) == []
+    one = hb.evolveHam_(s, ph, [0.1])
+    assert len(one) == 1 and maxerr(one[0].phsPositions, p1.phsPositions) < TOL
+    c1 = hb.stepHamC(0.1, s, c0)
+    assert maxerr(c1.cfgVelocities, o.velocities(qo, po)) < 1e-9
+
+
+def test_flags_on_singular_mass_matrix():
+    """two-body at r = 0 has J^T W J singular: reference `inv` would throw; we flag, never abort."""
+    g = hb.systems.builtin(hb.systems.TWO_BODY)
+    y = np.array([[0.0, 0.3, 0.1, 1.0], [2.0, 0.3, 0.1, 1.0]])
+    fl = np.zeros(2, np.int32)
+    g.batch_ham_eqs(y, flags=fl)
+    assert fl[0] != 0 and fl[1] == 0
+    with pytest.raises(hb.NumericError):
+        hb.hamEqs(g, hb.Phase([0.0, 0.3], [0.1, 1.0]))
+
+
+def test_init_random_matches_oracle(oracle_mod):
+    import torch
+    g, o = systems_for("double_pendulum", oracle_mod)
+    lo, hi = BOXES["double_pendulum"][1:]
+    y = g.batch_init_random(SEED, 5, 1000, lo, hi)
+    torch.cuda.synchronize()
+    assert np.array_equal(y.cpu().numpy(), o.init_random(SEED, 5, 1000, lo, hi))
+    ys = g.batch_init_random(SEED, 5, 1000, lo, hi, layout=L.SOA)
+    assert np.array_equal(ys.cpu().numpy().T, y.cpu().numpy())
