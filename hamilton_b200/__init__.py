@@ -10,5 +10,6 @@ from .api import (System, Config, Phase, Cfg, Phs, mkSystem, mkSystem_, underlyi
                   lagrangian, velocities, fromPhase, keP, hamiltonian, hamEqs, stepHam, evolveHam, evolveHam_,
                   stepHamC, evolveHamC, evolveHamC_)
 from . import systems                                                    # noqa: F401
+from . import ensemble                                                   # noqa: F401
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -63,6 +63,8 @@ def lib():
     L.hb_system_dims.argtypes = [vp, ip, ip]
     L.hb_system_source.argtypes = [vp, C.c_char_p, C.c_size_t]
     L.hb_system_source.restype = C.c_size_t
+    L.hb_system_params.argtypes = [vp, dp, i32]
+    L.hb_system_params.restype = i32
     L.hb_batch_ham_eqs.argtypes = [vp, i64, i32, i32, vp, vp, vp, vp]
     L.hb_batch_step.argtypes = [vp, i32, dbl, i32, i64, i32, i32, vp, vp, vp, vp]
     L.hb_batch_evolve.argtypes = [vp, i32, i32, i64, i32, i32, vp, dp, i32, vp, vp, vp]
@@ -102,7 +104,7 @@ def check(status):
 # every symbol include/hamilton_b200.h declares (checked by the CPU test-suite)
 ABI_SYMBOLS = [
     "hb_abi_version", "hb_last_error", "hb_device_count", "hb_set_device", "hb_system_builtin", "hb_system_from_tape",
-    "hb_system_free", "hb_system_dims", "hb_system_source", "hb_batch_ham_eqs", "hb_batch_step", "hb_batch_evolve",
+    "hb_system_free", "hb_system_dims", "hb_system_source", "hb_system_params", "hb_batch_ham_eqs", "hb_batch_step", "hb_batch_evolve",
     "hb_batch_to_phase", "hb_batch_from_phase", "hb_batch_energies", "hb_batch_underlying_pos", "hb_batch_init_random",
     "hb_underlying_pos", "hb_pe", "hb_momenta", "hb_velocities", "hb_ke_c", "hb_ke_p", "hb_lagrangian", "hb_hamiltonian",
     "hb_ham_eqs", "hb_step_ham", "hb_evolve_ham", "hb_step_ham_c", "hb_evolve_ham_c",

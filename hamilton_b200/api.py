@@ -88,6 +88,12 @@ class System:
         L.lib().hb_system_source(self._h, buf, need)
         return buf.value.decode()
 
+    def params(self):
+        n = L.lib().hb_system_params(self._h, None, 0)
+        buf = np.zeros(max(n, 1))
+        L.lib().hb_system_params(self._h, _p(buf), n)
+        return buf[:n]
+
     # ---- batched entry points ---------------------------------------------------------------
     def _io(self, x, name):
         """Returns (pointer, memspace, stream, device_ctx, keepalive, kind) for numpy or torch-cuda input."""

@@ -31,7 +31,7 @@ const char hb_engine_src[] = R"HBENGINE(
 // NVRTC for tape systems, so it must not include any standard header.
 #pragma once
 
-#define HB_MAXP 32
+#define HB_MAXP 64
 #define HB_DEV __device__ __forceinline__
 
 #ifndef HAMILTON_B200_H   // same values as the enum in include/hamilton_b200.h (not includable under NVRTC)
@@ -93,6 +93,70 @@ HB_DEV void hb_store(double* __restrict__ base, long long i, long long N, int la
 }
 HB_DEV bool hb_finite(double x) { return (__double2hiint(x) & 0x7ff00000) != 0x7ff00000; }
 
+// ------------------------------------------------------------------------ fp64 primitives --
+// The FP64 pipe (64 FMA/clk/SM) and the issue slots are what bound this engine, so the two
+// transcendental-class primitives every mechanical system leans on are hand-written:
+//
+// hb_sincos: Cody-Waite reduction by pi/2 (round-to-nearest via the 1.5*2^52 magic constant — no
+// F2I/I2F conversions), then the classic degree-13/14 minimax kernels on [-pi/4, pi/4] evaluated
+// with all coefficients taken straight from the constant bank as DFMA operands (CUDA's libdevice
+// version spends ~28 UMOV/IMAD issue slots per call materialising 64-bit immediates).  Max abs error
+// 1.8e-16 for |x| < 1e5 (checked against long double on the host); larger arguments take the
+// library slow path (Payne-Hanek).
+static __device__ __constant__ double hb_kSC[16] = {
+    6.36619772367581382433e-01,   // 0  2/pi
+    6755399441055744.0,           // 1  1.5 * 2^52
+    1.5707963267948966e+00,       // 2  pi/2 hi
+    6.123233995736766036e-17,     // 3  pi/2 lo
+    1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06,     // 4..9  sin kernel S6..S1
+    -1.98412698298579493134e-04, 8.33333333332248946124e-03, -1.66666666666666324348e-01,
+    -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07,    // 10..15 cos kernel C6..C1
+    2.48015872894767294178e-05, -1.38888888888741095749e-03, 4.16666666666666019037e-02};
+
+static __device__ __noinline__ double2 hb_sincos_slow(double x) { double2 r; sincos(x, &r.x, &r.y); return r; }
+
+HB_DEV void hb_sincos(double x, double* sp, double* cp) {
+  if (!(fabs(x) < 1.0e5)) { const double2 r = hb_sincos_slow(x); *sp = r.x; *cp = r.y; return; }   // rare: huge or non-finite argument
+  const double t = fma(x, hb_kSC[0], hb_kSC[1]);
+  const int k = __double2loint(t);
+  const double kf = t - hb_kSC[1];
+  double r = fma(-kf, hb_kSC[2], x);
+  r = fma(-kf, hb_kSC[3], r);
+  const double z = r * r;
+  double ps = fma(z, hb_kSC[4], hb_kSC[5]);
+  double pc = fma(z, hb_kSC[10], hb_kSC[11]);
+  ps = fma(z, ps, hb_kSC[6]);
+  pc = fma(z, pc, hb_kSC[12]);
+  ps = fma(z, ps, hb_kSC[7]);
+  pc = fma(z, pc, hb_kSC[13]);
+  ps = fma(z, ps, hb_kSC[8]);
+  pc = fma(z, pc, hb_kSC[14]);
+  ps = fma(z, ps, hb_kSC[9]);
+  pc = fma(z, pc, hb_kSC[15]);
+  const double sr = fma(z * r, ps, r);
+  const double cr = fma(z * z, pc, fma(z, -0.5, 1.0));
+  double s0 = (k & 1) ? cr : sr, c0 = (k & 1) ? sr : cr;
+  // sign flips on the high word: s negated in quadrants 2,3; c negated in quadrants 1,2
+  s0 = __hiloint2double(__double2hiint(s0) ^ ((k & 2) << 30), __double2loint(s0));
+  c0 = __hiloint2double(__double2hiint(c0) ^ (((k + 1) & 2) << 30), __double2loint(c0));
+  *sp = s0;
+  *cp = c0;
+}
+HB_DEV double hb_sin(double x) { double s, c; hb_sincos(x, &s, &c); return s; }
+HB_DEV double hb_cos(double x) { double s, c; hb_sincos(x, &s, &c); return c; }
+
+// hb_rcp: 1/d for the LDL^T pivots.  MUFU.RCP64H seed + two Newton steps (<= 1 ulp); no
+// denormal/overflow slow path: a pivot that needs one is flagged HB_FLAG_NOT_SPD / NONFINITE anyway.
+HB_DEV double hb_rcp(double d) {
+  double x;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+  double e = fma(-d, x, 1.0);
+  x = fma(x, e, x);
+  e = fma(-d, x, 1.0);
+  x = fma(x, e, x);
+  return x;
+}
+
 // Compile-time loop: f(HbIdx<B>{}), ..., f(HbIdx<E-1>{}).  The Sys index tables are queried with
 // true constant expressions (`if constexpr`), so structural zeros cost nothing — not even
 // front-end time — and the emitted code contains only the surviving FMAs.
@@ -143,7 +207,7 @@ HB_DEV void hb_ldlt(double* A, double* invd, int& flag) {
     }
     if (!(d > 0.0)) flag |= HB_FLAG_NOT_SPD;
     A[hb_tri(j, j)] = d;
-    const double id = 1.0 / d;
+    const double id = hb_rcp(d);
     invd[j] = id;
 #pragma unroll
     for (int i = j + 1; i < N; i++) {
@@ -595,11 +659,16 @@ HB_DEV void hb_body_init_random(const HbKArgs& a) {
 #define HB_K_UPOS 8
 #define HB_K_COUNT 9
 
+#ifndef HB_BLOCK
 #define HB_BLOCK 128
+#endif
+#ifndef HB_MINB_RK4
+#define HB_MINB_RK4 1   // min resident CTAs/SM requested for the RK4 kernels (register cap = 65536 / (128 * MINB))
+#endif
 
 // Instantiates the per-system __global__ kernels with C linkage names PFX_<kind>.
 #define HB_DEFINE_KERNELS(SYS, PFX)                                                                         \
-  extern "C" __global__ void __launch_bounds__(HB_BLOCK) PFX##_step_rk4(const __grid_constant__ HbKArgs a) { hb_body_step_rk4<SYS>(a); }      \
+  extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINB_RK4) PFX##_step_rk4(const __grid_constant__ HbKArgs a) { hb_body_step_rk4<SYS>(a); }      \
   extern "C" __global__ void __launch_bounds__(HB_BLOCK) PFX##_step_rkf45(const __grid_constant__ HbKArgs a) { hb_body_step_rkf45<SYS>(a); }  \
   extern "C" __global__ void __launch_bounds__(HB_BLOCK) PFX##_evolve_rk4(const __grid_constant__ HbKArgs a) { hb_body_evolve<SYS, false>(a); } \
   extern "C" __global__ void __launch_bounds__(HB_BLOCK) PFX##_evolve_rkf45(const __grid_constant__ HbKArgs a) { hb_body_evolve<SYS, true>(a); } \

@@ -20,7 +20,7 @@
 #include "sysgen.hpp"
 
 // ---- mirrors of the device-side declarations in engine/hb_engine.cuh (kept in sync by a static_assert in aot_kernels.cu)
-#define HB_MAXP 32
+#define HB_MAXP 64
 struct HbKArgs {
   const double* in; double* out; int* flags; const double* ts;
   long long N; double dt; int nsteps; int layout; int s; int substeps;
@@ -110,8 +110,14 @@ bool nvrtc_compile(const std::string& src, const std::string& arch, std::vector<
   nvrtcResult r = g_nvrtc.CreateProgram(&prog, src.c_str(), "hb_jit_system.cu", 1, hdr_src, hdr_name);
   if (r != NVRTC_SUCCESS) { log = std::string("nvrtcCreateProgram: ") + g_nvrtc.GetErrorString(r); return false; }
   std::string a = "--gpu-architecture=" + arch;
-  const char* opts[] = {a.c_str(), "--std=c++17", "-lineinfo", "--fmad=true", "-default-device"};
-  r = g_nvrtc.CompileProgram(prog, 5, opts);
+  std::vector<std::string> extra;   // HB_JIT_DEFINES="HB_MINB_RK4=8,FOO=1": tuning experiments without a rebuild
+  if (const char* e = std::getenv("HB_JIT_DEFINES")) {
+    std::string s(e); size_t p0 = 0;
+    while (p0 <= s.size()) { size_t p1 = s.find(',', p0); if (p1 == std::string::npos) p1 = s.size(); if (p1 > p0) extra.push_back("-D" + s.substr(p0, p1 - p0)); p0 = p1 + 1; }
+  }
+  std::vector<const char*> opts = {a.c_str(), "--std=c++17", "-lineinfo", "--fmad=true", "-default-device"};
+  for (auto& x : extra) opts.push_back(x.c_str());
+  r = g_nvrtc.CompileProgram(prog, (int)opts.size(), opts.data());
   size_t ls = 0;
   g_nvrtc.GetProgramLogSize(prog, &ls);
   if (ls > 1) { log.resize(ls); g_nvrtc.GetProgramLog(prog, &log[0]); }
@@ -145,6 +151,7 @@ struct hb_system {
       return *fn ? HB_OK : fail(HB_ERR_INVALID, "no such AOT kernel");
     }
     std::lock_guard<std::mutex> lk(mu);
+    if (cubin.empty()) return fail(HB_ERR_COMPILE, "system was created with HB_JIT_SKIP_COMPILE: no device code");
     if (!loaded) {
       CU(cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
       for (int k = 0; k < K_COUNT; k++) {
@@ -192,10 +199,11 @@ thread_local Scratch g_scratch;
 
 hb_status launch(const void* fn, const HbKArgs& a, long long work_items, cudaStream_t st) {
   if (work_items <= 0) return HB_OK;
-  long long blocks = (work_items + HB_BLOCK - 1) / HB_BLOCK;
+  static const int block = [] { const char* e = std::getenv("HB_LAUNCH_BLOCK"); int b = e ? std::atoi(e) : HB_BLOCK; return (b >= 32 && b <= 1024) ? b : HB_BLOCK; }();
+  long long blocks = (work_items + block - 1) / block;
   if (blocks > 0x7fffffffLL) blocks = 0x7fffffffLL;
   void* args[] = {(void*)&a};
-  CU(cudaLaunchKernel(fn, dim3((unsigned)blocks), dim3(HB_BLOCK), args, 0, st));
+  CU(cudaLaunchKernel(fn, dim3((unsigned)blocks), dim3(block), args, 0, st));
   return HB_OK;
 }
 
@@ -306,7 +314,7 @@ hb_status hb_system_from_tape(int32_t m, int32_t n, const double* inertia, const
   *out = nullptr;
   if (!inertia || !f || !u) return fail(HB_ERR_INVALID, "null argument");
   if (n < 1 || n > HB_MAX_N || m < 1 || m > HB_MAX_M) return fail(HB_ERR_INVALID, "dimensions out of range (1 <= n <= 16, 1 <= m <= 48)");
-  if (n_params < 0 || n_params > HB_MAXP || (n_params > 0 && !params)) return fail(HB_ERR_INVALID, "bad params (at most 32)");
+  if (n_params < 0 || n_params > 32 || (n_params > 0 && !params)) return fail(HB_ERR_INVALID, "bad params (at most 32)");
   if (f->n_in != n || f->n_out != m || !f->ops || !f->outs || f->n_ops < 1) return fail(HB_ERR_TAPE, "f tape must map n inputs to m outputs");
   if (u->n_in != (u_on_cartesian ? m : n) || u->n_out != 1 || !u->ops || !u->outs || u->n_ops < 1)
     return fail(HB_ERR_TAPE, "u tape must map n (or m when u_on_cartesian) inputs to 1 output");
@@ -323,7 +331,8 @@ hb_status hb_system_from_tape(int32_t m, int32_t n, const double* inertia, const
   std::string tu = hb::jit_translation_unit(g, "hbk");
   std::vector<char> cubin;
   std::string log;
-  if (!nvrtc_compile(tu, jit_arch(), cubin, log)) return fail(HB_ERR_COMPILE, log);
+  const bool skip = std::getenv("HB_JIT_SKIP_COMPILE") != nullptr;   // diagnostics: symbolic stage only, system cannot launch
+  if (!skip && !nvrtc_compile(tu, jit_arch(), cubin, log)) return fail(HB_ERR_COMPILE, log);
   hb_system* s = new hb_system();
   s->m = m; s->n = n; s->builtin = -1;
   s->params.assign(params, params + n_params);
@@ -349,6 +358,13 @@ size_t hb_system_source(const hb_system* sys, char* buf, size_t cap) {
   size_t need = sys->source.size() + 1;
   if (buf && cap) { size_t k = need < cap ? need : cap; std::memcpy(buf, sys->source.c_str(), k - 1); buf[k - 1] = 0; }
   return need;
+}
+
+int32_t hb_system_params(const hb_system* sys, double* buf, int32_t cap) {
+  if (!sys) return 0;
+  const int32_t n = (int32_t)sys->params.size();
+  for (int32_t k = 0; buf && k < n && k < cap; k++) buf[k] = sys->params[k];
+  return n;
 }
 
 hb_status hb_batch_ham_eqs(const hb_system* sys, int64_t N, hb_layout layout, hb_memspace mem, const double* y, double* dy,
@@ -472,7 +488,8 @@ hb_status hb_velocities(const hb_system* sys, const double* q, const double* p, 
   NEED(sys, q, p, v);
   double c[2 * HB_MAX_N], y[2 * HB_MAX_N]; int32_t fl = 0;
   pack(sys, q, p, y);
-  hb_status rc = one_flag(hb_batch_from_phase(sys, 1, HB_LAYOUT_AOS, HB_MEM_HOST, y, c, &fl, nullptr), fl);
+  hb_status rc = hb_batch_from_phase(sys, 1, HB_LAYOUT_AOS, HB_MEM_HOST, y, c, &fl, nullptr);
+  rc = one_flag(rc, fl);
   if (rc) return rc;
   std::memcpy(v, c + sys->n, sizeof(double) * sys->n);
   return HB_OK;
@@ -480,7 +497,8 @@ hb_status hb_velocities(const hb_system* sys, const double* q, const double* p, 
 static hb_status energies_p(const hb_system* sys, const double* q, const double* p, double* o4) {
   double y[2 * HB_MAX_N]; int32_t fl = 0;
   pack(sys, q, p, y);
-  return one_flag(hb_batch_energies(sys, 1, HB_LAYOUT_AOS, HB_MEM_HOST, y, o4, &fl, nullptr), fl);
+  hb_status rc = hb_batch_energies(sys, 1, HB_LAYOUT_AOS, HB_MEM_HOST, y, o4, &fl, nullptr);
+  return one_flag(rc, fl);
 }
 static hb_status energies_c(const hb_system* sys, const double* q, const double* v, double* o4) {
   double p[HB_MAX_N];
@@ -504,7 +522,8 @@ hb_status hb_ham_eqs(const hb_system* sys, const double* q, const double* p, dou
   NEED(sys, q, p, dq, dp);
   double y[2 * HB_MAX_N], dy[2 * HB_MAX_N]; int32_t fl = 0;
   pack(sys, q, p, y);
-  hb_status rc = one_flag(hb_batch_ham_eqs(sys, 1, HB_LAYOUT_AOS, HB_MEM_HOST, y, dy, &fl, nullptr), fl);
+  hb_status rc = hb_batch_ham_eqs(sys, 1, HB_LAYOUT_AOS, HB_MEM_HOST, y, dy, &fl, nullptr);
+  rc = one_flag(rc, fl);
   if (rc) return rc;
   std::memcpy(dq, dy, sizeof(double) * sys->n); std::memcpy(dp, dy + sys->n, sizeof(double) * sys->n);
   return HB_OK;
@@ -513,7 +532,8 @@ hb_status hb_step_ham(const hb_system* sys, double r, const double* q, const dou
   NEED(sys, q, p, q_out, p_out);
   double y[2 * HB_MAX_N], yo[2 * HB_MAX_N]; int32_t fl = 0;
   pack(sys, q, p, y);
-  hb_status rc = one_flag(hb_batch_step(sys, HB_INTEG_RKF45_GSL, r, 1, 1, HB_LAYOUT_AOS, HB_MEM_HOST, y, yo, &fl, nullptr), fl);
+  hb_status rc = hb_batch_step(sys, HB_INTEG_RKF45_GSL, r, 1, 1, HB_LAYOUT_AOS, HB_MEM_HOST, y, yo, &fl, nullptr);
+  rc = one_flag(rc, fl);
   if (rc) return rc;
   std::memcpy(q_out, yo, sizeof(double) * sys->n); std::memcpy(p_out, yo + sys->n, sizeof(double) * sys->n);
   return HB_OK;
@@ -522,7 +542,8 @@ hb_status hb_evolve_ham(const hb_system* sys, const double* q0, const double* p0
   NEED(sys, q0, p0, ts, out);
   double y[2 * HB_MAX_N]; int32_t fl = 0;
   pack(sys, q0, p0, y);
-  return one_flag(hb_batch_evolve(sys, HB_INTEG_RKF45_GSL, 1, 1, HB_LAYOUT_AOS, HB_MEM_HOST, y, ts, s, out, &fl, nullptr), fl);
+  hb_status rc = hb_batch_evolve(sys, HB_INTEG_RKF45_GSL, 1, 1, HB_LAYOUT_AOS, HB_MEM_HOST, y, ts, s, out, &fl, nullptr);
+  return one_flag(rc, fl);
 }
 hb_status hb_step_ham_c(const hb_system* sys, double r, const double* q, const double* v, double* q_out, double* v_out) {
   NEED(sys, q, v, q_out, v_out);

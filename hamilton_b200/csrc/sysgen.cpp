@@ -87,11 +87,11 @@ struct Emitter {
           if (p.first >= 0 && p.second >= 0) {
             if (!done_sc.count(n.a)) {
               done_sc.insert(n.a);
-              os << "    double t" << p.first << ", t" << p.second << "; sincos(" << A() << ", &t" << p.first << ", &t"
+              os << "    double t" << p.first << ", t" << p.second << "; hb_sincos(" << A() << ", &t" << p.first << ", &t"
                  << p.second << ");\n";
             }
           } else {
-            fn1(n.op == Op::Sin ? "sin" : "cos");
+            fn1(n.op == Op::Sin ? "hb_sin" : "hb_cos");
           }
           break;
         }

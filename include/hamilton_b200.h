@@ -37,7 +37,7 @@ extern "C" {
 #define HB_ABI_VERSION 1
 #define HB_MAX_N 16      /* generalized coordinates per system            */
 #define HB_MAX_M 48      /* Cartesian coordinates per system              */
-#define HB_MAX_PARAMS 64 /* runtime parameters (HB_OP_PARAM leaves)       */
+#define HB_MAX_PARAMS 32 /* runtime parameters (HB_OP_PARAM leaves)       */
 
 typedef int32_t hb_status;
 enum {
@@ -147,6 +147,9 @@ hb_status hb_system_dims(const hb_system* sys, int32_t* m, int32_t* n);
 /* Generated CUDA source of the system's derivative code (diagnostics / docs).  Returns bytes
  * needed (including NUL); copies at most `cap`. */
 size_t hb_system_source(const hb_system* sys, char* buf, size_t cap);
+/* Runtime parameter vector the generated code reads as prm[k] (for built-ins: derived from the user
+ * parameters, e.g. two-body stores m1, m2, -(m2/mT), m1/mT, m1*m2).  Returns the count; copies at most `cap`. */
+int32_t hb_system_params(const hb_system* sys, double* buf, int32_t cap);
 
 /* ---- batched hot path ---------------------------------------------------------------------
  * All arrays hold N trajectories in `layout`, in `mem`; `stream` is a cudaStream_t passed as

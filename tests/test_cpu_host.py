@@ -1,0 +1,218 @@
+"""CPU suite, part 2: host logic of the product — the C-ABI library loads and exports every symbol the header
+declares, the symbolic system compiler's output is checked against the oracle by compiling the generated `Sys` struct
+as host code, tape validation errors, the Python mirror's API edge cases, and the N>1 sharding/gather plumbing over gloo.
+No compute entry point is exercised without a GPU (they must refuse: there is no CPU fallback)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+import hamilton_b200 as hb
+from hamilton_b200 import _lib as L
+from hamilton_b200 import num
+from tests.common import BOXES, maxerr, random_phases
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+NAMES = list(BOXES)
+
+
+def test_abi_library_exports_every_declared_symbol():
+    lib = L.lib()
+    assert lib.hb_abi_version() == 1
+    hdr = open(os.path.join(ROOT, "include", "hamilton_b200.h")).read()
+    declared = set(re.findall(r"\b(hb_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"hb_op", "hb_tape", "hb_status"}
+    assert declared == set(L.ABI_SYMBOLS), declared ^ set(L.ABI_SYMBOLS)
+    for s in declared:
+        assert hasattr(lib, s), s
+    assert lib.hb_last_error() is not None
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    s = hb.systems.builtin(hb.systems.DOUBLE_PENDULUM)
+    with pytest.raises(hb.NoDeviceError):
+        hb.hamEqs(s, hb.Phase([1.0, 0.0], [0.0, 0.5]))
+    with pytest.raises(hb.NoDeviceError):
+        s.batch_step(np.zeros((4, 4)), 0.01)
+    n = C.c_int32(-1)
+    assert L.lib().hb_device_count(C.byref(n)) == L.ERR_NO_DEVICE and n.value == 0
+
+
+def _host_eval(system, name, tmp):
+    """Compiles the generated Sys struct as host C++ and returns eval(q) -> (J, H, gU, x, U, w)."""
+    src = os.path.join(tmp, name + "_sys.inc")
+    with open(src, "w") as f:
+        f.write(system.source())
+    sname = re.search(r"struct (\w+) \{", system.source()).group(1)
+    so = os.path.join(tmp, name + ".so")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", '-DSYS_SOURCE="%s"' % src, "-DSYS_NAME=" + sname,
+                           os.path.join(ROOT, "tests", "host_eval_harness.cpp"), "-o", so])
+    lib = C.CDLL(so)
+    d = (C.c_int * 4)()
+    lib.dims(d)
+    m, n = d[0], d[1]
+    assert (m, n) == (system.m, system.n)
+    prm = np.r_[system.params(), 0.0]
+    dp = C.POINTER(C.c_double)
+
+    def ev(q):
+        q = np.ascontiguousarray(q, float)
+        J, H, gU, x, U, w = np.zeros((m, n)), np.zeros((n, m, n)), np.zeros(n), np.zeros(m), C.c_double(), np.zeros(m)
+        lib.eval(prm.ctypes.data_as(dp), q.ctypes.data_as(dp), J.ctypes.data_as(dp), H.ctypes.data_as(dp), gU.ctypes.data_as(dp),
+                 x.ctypes.data_as(dp), C.byref(U), w.ctypes.data_as(dp))
+        return J, H, gU, x, U.value, w
+    return ev, (d[2], d[3])
+
+
+@pytest.mark.parametrize("name", NAMES)
+@pytest.mark.parametrize("kind", ["aot", "jit"])
+def test_system_compiler_output_matches_oracle_derivatives(name, kind, oracle_mod):
+    """Symbolic 2nd-order forward AD (csrc/symbolic.cpp + sysgen.cpp) vs the oracle's dense jets: J, every Hessian slice,
+    grad U, f, U and the inertia vector, for the AOT built-ins (runtime PARAM leaves) and tape systems (literals)."""
+    sid = BOXES[name][0]
+    if kind == "jit":
+        os.environ["HB_JIT_SKIP_COMPILE"] = "1"      # symbolic stage only: NVRTC is exercised by test_nvrtc_*
+        try:
+            g = hb.systems.from_def(hb.systems.DEFS[sid]())
+        finally:
+            del os.environ["HB_JIT_SKIP_COMPILE"]
+    else:
+        g = hb.systems.builtin(sid)
+    o = oracle_mod.OracleSystem.builtin(sid)
+    with tempfile.TemporaryDirectory() as tmp:
+        ev, (nj, nh) = _host_eval(g, name + kind, tmp)
+        for r in random_phases(name, 5):
+            q = r[: o.n]
+            J, H, gU, x, U, w = ev(q)
+            assert maxerr(J, o.jacobian(q)) < 1e-13
+            assert maxerr(H, o.hessian(q)) < 1e-13
+            assert maxerr(gU, o.potential_grad(q)) < 1e-13
+            assert maxerr(x, o.underlying_pos(q)) < 1e-13 and abs(U - o.pe(q)) < 1e-13 * (1 + abs(U))
+        # sparsity is structural: chain12's Hessian tensor is "diagonal" (156 of 3456 entries), its J lower-triangular
+        if name == "chain12":
+            assert (nj, nh) == (156, 156)
+        if name == "room":
+            assert (nj, nh) == (2, 0)
+
+
+def test_nvrtc_compiles_a_tape_system_without_a_gpu():
+    """hb_system_from_tape = symbolic AD + CUDA source + NVRTC (sm_100a cubin); needs no device until the first launch."""
+    s = hb.mkSystem_([1.0, 1.0], lambda q: [num.sin(q[0]), 0.5 - num.cos(q[0])], lambda x: x[1], n=1)
+    assert (s.m, s.n) == (2, 1)
+    assert "hb_sincos" in s.source() and "struct HbSysJit" in s.source()
+
+
+def test_tape_validation_errors():
+    lib = L.lib()
+
+    def mk(ops, outs, n_in):
+        arr = (L.HbOp * len(ops))()
+        for k, (op, a, b, c) in enumerate(ops):
+            arr[k].op, arr[k].a, arr[k].b, arr[k].c = op, a, b, c
+        o = (C.c_int32 * len(outs))(*outs)
+        return L.HbTape(n_in, len(ops), arr, len(outs), o), (arr, o)
+    w = (C.c_double * 1)(1.0)
+    good_u, k0 = mk([(num.OP_INPUT, 0, 0, 0.0)], [0], 1)
+    h = C.c_void_p()
+    # forward reference
+    bad, k1 = mk([(num.OP_INPUT, 0, 0, 0.0), (num.OP_ADD, 0, 5, 0.0)], [1], 1)
+    assert lib.hb_system_from_tape(1, 1, w, C.byref(bad), C.byref(good_u), 0, None, 0, C.byref(h)) == L.ERR_TAPE
+    assert b"earlier node" in lib.hb_last_error()
+    # unknown opcode
+    bad, k2 = mk([(99, 0, 0, 0.0)], [0], 1)
+    assert lib.hb_system_from_tape(1, 1, w, C.byref(bad), C.byref(good_u), 0, None, 0, C.byref(h)) == L.ERR_TAPE
+    # wrong arity of f
+    assert lib.hb_system_from_tape(2, 1, w, C.byref(good_u), C.byref(good_u), 0, None, 0, C.byref(h)) == L.ERR_TAPE
+    # dimensions out of range, null pointers
+    assert lib.hb_system_from_tape(1, 17, w, C.byref(good_u), C.byref(good_u), 0, None, 0, C.byref(h)) == L.ERR_INVALID
+    assert lib.hb_system_builtin(99, None, 0, C.byref(h)) == L.ERR_INVALID
+    assert lib.hb_batch_step(None, 0, 0.01, 1, 1, 0, 0, None, None, None, None) == L.ERR_INVALID
+
+
+def test_python_mirror_argument_checks():
+    s = hb.systems.builtin(hb.systems.DOUBLE_PENDULUM)
+    assert (s.m, s.n) == (4, 2)
+    assert np.allclose(s.params(), [1.0, 1.0])
+    assert np.allclose(hb.systems.builtin(hb.systems.TWO_BODY).params(), [5.0, 0.5, -(0.5 / 5.5), 5.0 / 5.5, 2.5])
+    with pytest.raises(ValueError):
+        hb.evolveHam(s, hb.Phase([0, 0], [0, 0]), [0.0])          # the type-level `2 <= s`
+    assert hb.evolveHam_(s, hb.Phase([0, 0], [0, 0]), []) == []      # evolveHam' [] = []
+    assert hb.evolveHamC_(s, hb.Config([0, 0], [0, 0]), []) == []
+    with pytest.raises(ValueError):
+        hb.hamEqs(s, hb.Phase([0.0], [0.0]))                        # wrong vector length
+    with pytest.raises(ValueError):
+        s.batch_step(np.zeros((4, 3)), 0.01)
+    with pytest.raises(ValueError):
+        hb.mkSystem([1, 1], lambda q: [q[0]], lambda q: q[0], n=1)   # f returns 1 coordinate, inertia has 2
+
+
+def test_tracer_records_haskell_operator_split():
+    """x ** 2.0 -> POW (Floating (**)), x ** 2 -> POWI (Num (^)); constants lift like fromInteger/realToFrac."""
+    t, outs = num.trace(lambda q: [q[0] ** 2.0, q[0] ** 3, 2 * q[0] - 1, num.atan2(q[0], 1.0)], 1)
+    ops = [o[0] for o in t.ops]
+    assert num.OP_POW in ops and num.OP_POWI in ops and num.OP_ATAN2 in ops and len(outs) == 4
+    assert num.sin(0.5) == np.sin(0.5)                               # same functions on plain floats
+    import sympy
+    assert num.cos(sympy.Symbol("x")).diff(sympy.Symbol("x")) == -sympy.sin(sympy.Symbol("x"))
+
+
+def test_shard_partition():
+    for n, w in [(10, 3), (8388608, 8), (5, 8), (0, 2)]:
+        parts = [hb.ensemble.shard(n, r, w) for r in range(w)]
+        assert parts[0][0] == 0 and sum(c for _, c in parts) == n
+        for (f0, c0), (f1, _) in zip(parts, parts[1:]):
+            assert f0 + c0 == f1
+
+
+def _gloo_worker(rank, world, port, n_total, q):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from oracle import oracle as O
+    import hamilton_b200 as hbm
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    o = O.OracleSystem.builtin(O.DOUBLE_PENDULUM)
+    lo, hi = BOXES["double_pendulum"][1:]
+    first, count = hbm.ensemble.shard(n_total, rank, world)
+    y = o.init_random(0x48414D49, first, count, lo, hi)            # what batch_init_random generates on each GPU
+    out, _ = o.batch_step(y, 0, 0.01, 2)                             # stand-in for the GPU step (tests may use the oracle)
+    full = hbm.ensemble.gather_final(torch.from_numpy(out))
+    q.put((rank, full.numpy()))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_total", [64, 37])
+def test_ensemble_gather_world_size_2_gloo(n_total, oracle_mod):
+    """N>1 path on CPU: block sharding + counter-based init + all-gather reassemble exactly the single-process result."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + n_total
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, n_total, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    o = oracle_mod.OracleSystem.builtin(1)
+    lo, hi = BOXES["double_pendulum"][1:]
+    want, _ = o.batch_step(o.init_random(0x48414D49, 0, n_total, lo, hi), 0, 0.01, 2)
+    assert np.array_equal(res[0], want) and np.array_equal(res[1], want)
+
+
+def test_bench_reference_arm_runs_on_cpu():
+    out = subprocess.check_output([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1"],
+                                  cwd=ROOT, text=True)
+    import json
+    j = json.loads(out.strip().splitlines()[-1])
+    assert j["impl"] == "reference" and j["value"] > 0 and j["cpu_baseline"]["kind"] == "port" and j["unit"] == "steps/s"

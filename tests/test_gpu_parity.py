@@ -205,3 +205,49 @@ def test_init_random_matches_oracle(oracle_mod):
     assert np.array_equal(y.cpu().numpy(), o.init_random(SEED, 5, 1000, lo, hi))
     ys = g.batch_init_random(SEED, 5, 1000, lo, hi, layout=L.SOA)
     assert np.array_equal(ys.cpu().numpy().T, y.cpu().numpy())
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_gpu_vs_committed_golden_vectors(name):
+    """The CUDA path against tests/golden/oracle_vectors.json (oracle output frozen by oracle/make_golden.py)."""
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "oracle_vectors.json")) as f:
+        g = json.load(f)[name]
+    n = g["n"]
+    un = lambda v, shape: np.array([float.fromhex(s) for s in v]).reshape(shape)   # noqa: E731
+    y = un(g["y"], (4, 2 * n))
+    s = hb.systems.builtin(BOXES[name][0])
+    assert maxerr(s.batch_ham_eqs(y), un(g["ham_eqs"], (4, 2 * n))) < TOL
+    assert maxerr(s.batch_step(y, 0.01, 1, integ=L.RK4), un(g["rk4_1"], (4, 2 * n))) < TOL
+    assert maxerr(s.batch_step(y, 0.01, 10, integ=L.RK4), un(g["rk4_10"], (4, 2 * n))) < 10 * TOL
+    assert maxerr(s.batch_step(y, 0.01, 1, integ=L.RKF45_GSL), un(g["step_ham"], (4, 2 * n))) < TOL
+    assert maxerr(s.batch_step(y, 1.0 / 12, 1, integ=L.RKF45_GSL), un(g["step_ham_demo"], (4, 2 * n))) < 1e-9
+    ts = un(g["ts"], (-1,))
+    ev = s.batch_evolve(y, ts, integ=L.RKF45_GSL)                   # (s, 4, 2n)
+    assert maxerr(np.transpose(ev, (1, 0, 2)), un(g["evolve"], (4, len(ts), 2 * n))) < 1e-9
+    e = s.batch_energies(y)
+    assert maxerr(e[:, :3], un(g["energies"], (4, 3))) < TOL
+    assert maxerr(s.batch_underlying_pos(np.ascontiguousarray(y[:, :n])), un(g["upos"], (4, g["m"]))) < TOL
+
+
+def test_large_batch_properties_at_full_size():
+    """BASELINE configs[1] at full size (1,048,576 trajectories): size-independent properties instead of an oracle run —
+    energy conservation of RK4 (O(dt^4) per unit time), time reversal, and agreement of the AOS and SOA paths."""
+    import torch
+    s = hb.systems.builtin(hb.systems.DOUBLE_PENDULUM)
+    lo, hi = BOXES["double_pendulum"][1:]
+    N = 1 << 20
+    y0 = s.batch_init_random(SEED, 0, N, lo, hi)
+    e0 = s.batch_energies(y0)[:, 2]
+    y1 = s.batch_step(y0, 0.001, 100, integ=L.RK4)
+    e1 = s.batch_energies(y1)[:, 2]
+    assert float((e1 - e0).abs().max()) < 1e-7
+    back = y1.clone(); back[:, 2:] *= -1
+    y2 = s.batch_step(back, 0.001, 100, integ=L.RK4); y2[:, 2:] *= -1
+    assert float((y2 - y0).abs().max()) < 1e-7
+    soa = s.batch_step(y0.t().contiguous(), 0.001, 100, integ=L.RK4, layout=L.SOA)
+    assert torch.equal(soa.t().contiguous(), y1)
+    fl = torch.zeros(N, dtype=torch.int32, device=y0.device)
+    s.batch_step(y0, 0.01, 1, integ=L.RKF45_GSL, flags=fl)
+    assert int(fl.sum()) == 0
