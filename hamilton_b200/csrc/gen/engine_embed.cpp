@@ -20,18 +20,24 @@ const char hb_engine_src[] = R"HBENGINE(
 //     static constexpr int jidx(i, j);  // position of J[i][j] in the packed list, -1 if J[i][j] == 0
 //     static constexpr int jrow(e), jcol(e);
 //     static constexpr int hrow(e), hj(e), hk(e);   // H entry e is d2 f_hrow / dq_hj dq_hk, hj <= hk
+//     static constexpr bool TRIG;       // uses sin/cos (needs the shared-memory table)
 //     static void inertia(prm, w[M]);
-//     static void derivs(prm, q, Jv[NJ], Hv[NH], gU[N]);   // everything hamEqs needs
-//     static void jac(prm, q, Jv[NJ]);
-//     static void jac_pot(prm, q, Jv[NJ], U);
-//     static void pos(prm, q, x[M]);
+//     template <bool FAST> static void derivs(cx, prm, q, Jv[NJ], Hv[NH], gU[N]);   // everything hamEqs needs
+//     template <bool FAST> static void jac(cx, prm, q, Jv[NJ]);
+//     template <bool FAST> static void jac_pot(cx, prm, q, Jv[NJ], U);
+//     template <bool FAST> static void pos(cx, prm, q, x[M]);
 //   };
+// FAST selects the hand-written fp64 primitives below; FAST=false is the out-of-line retry with
+// libdevice math for the rare trajectory whose arguments leave the fast primitives' domain.
 //
 // This header is compiled ahead of time by nvcc for the built-in systems and at run time by
 // NVRTC for tape systems, so it must not include any standard header.
 #pragma once
 
 #define HB_MAXP 64
+#ifndef HB_BLOCK
+#define HB_BLOCK 128      // threads per CTA of every kernel (the host launches exactly this)
+#endif
 #define HB_DEV __device__ __forceinline__
 
 #ifndef HAMILTON_B200_H   // same values as the enum in include/hamilton_b200.h (not includable under NVRTC)
@@ -49,6 +55,7 @@ struct HbKArgs {
   const double* ts;       // evolve: time grid on the device
   long long N;            // trajectories
   double dt;              // step size
+  double dt6;             // dt / 6 (host-computed: keeps a full-precision division out of every thread)
   int nsteps;             // steps per launch
   int layout;             // 0 = AOS y[i*D+c], 1 = SOA y[c*N+i]
   int s;                  // evolve: number of grid points
@@ -92,60 +99,135 @@ HB_DEV void hb_store(double* __restrict__ base, long long i, long long N, int la
   }
 }
 HB_DEV bool hb_finite(double x) { return (__double2hiint(x) & 0x7ff00000) != 0x7ff00000; }
+template <int D>
+HB_DEV void hb_copy(const double* src, double (&dst)[D]) {
+#pragma unroll
+  for (int c = 0; c < D; c++) dst[c] = src[c];
+}
 
 // ------------------------------------------------------------------------ fp64 primitives --
 // The FP64 pipe (64 FMA/clk/SM) and the issue slots are what bound this engine, so the two
-// transcendental-class primitives every mechanical system leans on are hand-written:
+// transcendental-class primitives every mechanical system leans on are hand-written.
 //
-// hb_sincos: Cody-Waite reduction by pi/2 (round-to-nearest via the 1.5*2^52 magic constant — no
-// F2I/I2F conversions), then the classic degree-13/14 minimax kernels on [-pi/4, pi/4] evaluated
-// with all coefficients taken straight from the constant bank as DFMA operands (CUDA's libdevice
-// version spends ~28 UMOV/IMAD issue slots per call materialising 64-bit immediates).  Max abs error
-// 1.8e-16 for |x| < 1e5 (checked against long double on the host); larger arguments take the
-// library slow path (Payne-Hanek).
-static __device__ __constant__ double hb_kSC[16] = {
-    6.36619772367581382433e-01,   // 0  2/pi
+// hb_sincos<FAST=true>: x = k*(pi/64) + r with k = rint(x*64/pi) obtained from the 1.5*2^52 magic
+// constant (no F2I/I2F), two-term Cody-Waite reduction, |r| <= pi/128; (sin, cos)(k*pi/64) come from
+// a 128-entry table staged in shared memory (one LDS.128), sin r and cos r - 1 from 3-term
+// polynomials, combined by the angle-addition formulas: 16 DFMA-class instructions instead of the
+// ~24 + ~28 immediate-materialising moves of libdevice's sincos, no quadrant logic, no branch.
+// Arguments with |x| >= 1e5 (or non-finite) only set cx.oob; the caller then redoes that
+// trajectory on the out-of-line slow path (FAST=false: libdevice sincos with Payne-Hanek reduction).
+// Max abs error of the fast path ~2e-16 (checked against long double on the host).
+struct HbCtx {
+  const double2* tab;   // shared-memory copy of hb_kSinCosTab (fast path only)
+  unsigned oob;         // set when a fast-path primitive saw an argument outside its domain
+};
+
+static __device__ const double2 hb_kSinCosTab[128] = {   // {sin, cos}(k*pi/64), correctly rounded
+    {0, 1}, {0.049067674327418015, 0.99879545620517241},
+    {0.098017140329560604, 0.99518472667219693}, {0.14673047445536175, 0.98917650996478101},
+    {0.19509032201612828, 0.98078528040323043}, {0.2429801799032639, 0.97003125319454397},
+    {0.29028467725446239, 0.95694033573220882}, {0.33688985339222005, 0.94154406518302081},
+    {0.38268343236508978, 0.92387953251128674}, {0.42755509343028208, 0.90398929312344334},
+    {0.47139673682599764, 0.88192126434835505}, {0.51410274419322177, 0.85772861000027212},
+    {0.55557023301960218, 0.83146961230254524}, {0.59569930449243336, 0.80320753148064494},
+    {0.63439328416364549, 0.77301045336273699}, {0.67155895484701844, 0.74095112535495911},
+    {0.70710678118654757, 0.70710678118654757}, {0.74095112535495911, 0.67155895484701844},
+    {0.77301045336273699, 0.63439328416364549}, {0.80320753148064494, 0.59569930449243336},
+    {0.83146961230254524, 0.55557023301960218}, {0.85772861000027212, 0.51410274419322177},
+    {0.88192126434835505, 0.47139673682599764}, {0.90398929312344334, 0.42755509343028208},
+    {0.92387953251128674, 0.38268343236508978}, {0.94154406518302081, 0.33688985339222005},
+    {0.95694033573220882, 0.29028467725446239}, {0.97003125319454397, 0.2429801799032639},
+    {0.98078528040323043, 0.19509032201612828}, {0.98917650996478101, 0.14673047445536175},
+    {0.99518472667219693, 0.098017140329560604}, {0.99879545620517241, 0.049067674327418015},
+    {1, 0}, {0.99879545620517241, -0.049067674327418015},
+    {0.99518472667219693, -0.098017140329560604}, {0.98917650996478101, -0.14673047445536175},
+    {0.98078528040323043, -0.19509032201612828}, {0.97003125319454397, -0.2429801799032639},
+    {0.95694033573220882, -0.29028467725446239}, {0.94154406518302081, -0.33688985339222005},
+    {0.92387953251128674, -0.38268343236508978}, {0.90398929312344334, -0.42755509343028208},
+    {0.88192126434835505, -0.47139673682599764}, {0.85772861000027212, -0.51410274419322177},
+    {0.83146961230254524, -0.55557023301960218}, {0.80320753148064494, -0.59569930449243336},
+    {0.77301045336273699, -0.63439328416364549}, {0.74095112535495911, -0.67155895484701844},
+    {0.70710678118654757, -0.70710678118654757}, {0.67155895484701844, -0.74095112535495911},
+    {0.63439328416364549, -0.77301045336273699}, {0.59569930449243336, -0.80320753148064494},
+    {0.55557023301960218, -0.83146961230254524}, {0.51410274419322177, -0.85772861000027212},
+    {0.47139673682599764, -0.88192126434835505}, {0.42755509343028208, -0.90398929312344334},
+    {0.38268343236508978, -0.92387953251128674}, {0.33688985339222005, -0.94154406518302081},
+    {0.29028467725446239, -0.95694033573220882}, {0.2429801799032639, -0.97003125319454397},
+    {0.19509032201612828, -0.98078528040323043}, {0.14673047445536175, -0.98917650996478101},
+    {0.098017140329560604, -0.99518472667219693}, {0.049067674327418015, -0.99879545620517241},
+    {0, -1}, {-0.049067674327418015, -0.99879545620517241},
+    {-0.098017140329560604, -0.99518472667219693}, {-0.14673047445536175, -0.98917650996478101},
+    {-0.19509032201612828, -0.98078528040323043}, {-0.2429801799032639, -0.97003125319454397},
+    {-0.29028467725446239, -0.95694033573220882}, {-0.33688985339222005, -0.94154406518302081},
+    {-0.38268343236508978, -0.92387953251128674}, {-0.42755509343028208, -0.90398929312344334},
+    {-0.47139673682599764, -0.88192126434835505}, {-0.51410274419322177, -0.85772861000027212},
+    {-0.55557023301960218, -0.83146961230254524}, {-0.59569930449243336, -0.80320753148064494},
+    {-0.63439328416364549, -0.77301045336273699}, {-0.67155895484701844, -0.74095112535495911},
+    {-0.70710678118654757, -0.70710678118654757}, {-0.74095112535495911, -0.67155895484701844},
+    {-0.77301045336273699, -0.63439328416364549}, {-0.80320753148064494, -0.59569930449243336},
+    {-0.83146961230254524, -0.55557023301960218}, {-0.85772861000027212, -0.51410274419322177},
+    {-0.88192126434835505, -0.47139673682599764}, {-0.90398929312344334, -0.42755509343028208},
+    {-0.92387953251128674, -0.38268343236508978}, {-0.94154406518302081, -0.33688985339222005},
+    {-0.95694033573220882, -0.29028467725446239}, {-0.97003125319454397, -0.2429801799032639},
+    {-0.98078528040323043, -0.19509032201612828}, {-0.98917650996478101, -0.14673047445536175},
+    {-0.99518472667219693, -0.098017140329560604}, {-0.99879545620517241, -0.049067674327418015},
+    {-1, 0}, {-0.99879545620517241, 0.049067674327418015},
+    {-0.99518472667219693, 0.098017140329560604}, {-0.98917650996478101, 0.14673047445536175},
+    {-0.98078528040323043, 0.19509032201612828}, {-0.97003125319454397, 0.2429801799032639},
+    {-0.95694033573220882, 0.29028467725446239}, {-0.94154406518302081, 0.33688985339222005},
+    {-0.92387953251128674, 0.38268343236508978}, {-0.90398929312344334, 0.42755509343028208},
+    {-0.88192126434835505, 0.47139673682599764}, {-0.85772861000027212, 0.51410274419322177},
+    {-0.83146961230254524, 0.55557023301960218}, {-0.80320753148064494, 0.59569930449243336},
+    {-0.77301045336273699, 0.63439328416364549}, {-0.74095112535495911, 0.67155895484701844},
+    {-0.70710678118654757, 0.70710678118654757}, {-0.67155895484701844, 0.74095112535495911},
+    {-0.63439328416364549, 0.77301045336273699}, {-0.59569930449243336, 0.80320753148064494},
+    {-0.55557023301960218, 0.83146961230254524}, {-0.51410274419322177, 0.85772861000027212},
+    {-0.47139673682599764, 0.88192126434835505}, {-0.42755509343028208, 0.90398929312344334},
+    {-0.38268343236508978, 0.92387953251128674}, {-0.33688985339222005, 0.94154406518302081},
+    {-0.29028467725446239, 0.95694033573220882}, {-0.2429801799032639, 0.97003125319454397},
+    {-0.19509032201612828, 0.98078528040323043}, {-0.14673047445536175, 0.98917650996478101},
+    {-0.098017140329560604, 0.99518472667219693}, {-0.049067674327418015, 0.99879545620517241},
+};
+static __device__ __constant__ double hb_kSC[10] = {
+    20.371832715762604,           // 0  64/pi
     6755399441055744.0,           // 1  1.5 * 2^52
-    1.5707963267948966e+00,       // 2  pi/2 hi
-    6.123233995736766036e-17,     // 3  pi/2 lo
-    1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06,     // 4..9  sin kernel S6..S1
-    -1.98412698298579493134e-04, 8.33333333332248946124e-03, -1.66666666666666324348e-01,
-    -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07,    // 10..15 cos kernel C6..C1
-    2.48015872894767294178e-05, -1.38888888888741095749e-03, 4.16666666666666019037e-02};
+    0.04908738521234052,          // 2  pi/64 hi
+    1.9135106236677394e-18,       // 3  pi/64 lo
+    -1.0 / 6.0, 1.0 / 120.0, -1.0 / 5040.0,      // 4..6   sin r = r + r^3 (S1 + z (S2 + z S3))
+    -0.5, 1.0 / 24.0, -1.0 / 720.0};             // 7..9   cos r - 1 = z (C1 + z (C2 + z C3))
 
-static __device__ __noinline__ double2 hb_sincos_slow(double x) { double2 r; sincos(x, &r.x, &r.y); return r; }
-
-HB_DEV void hb_sincos(double x, double* sp, double* cp) {
-  if (!(fabs(x) < 1.0e5)) { const double2 r = hb_sincos_slow(x); *sp = r.x; *cp = r.y; return; }   // rare: huge or non-finite argument
-  const double t = fma(x, hb_kSC[0], hb_kSC[1]);
-  const int k = __double2loint(t);
-  const double kf = t - hb_kSC[1];
-  double r = fma(-kf, hb_kSC[2], x);
-  r = fma(-kf, hb_kSC[3], r);
-  const double z = r * r;
-  double ps = fma(z, hb_kSC[4], hb_kSC[5]);
-  double pc = fma(z, hb_kSC[10], hb_kSC[11]);
-  ps = fma(z, ps, hb_kSC[6]);
-  pc = fma(z, pc, hb_kSC[12]);
-  ps = fma(z, ps, hb_kSC[7]);
-  pc = fma(z, pc, hb_kSC[13]);
-  ps = fma(z, ps, hb_kSC[8]);
-  pc = fma(z, pc, hb_kSC[14]);
-  ps = fma(z, ps, hb_kSC[9]);
-  pc = fma(z, pc, hb_kSC[15]);
-  const double sr = fma(z * r, ps, r);
-  const double cr = fma(z * z, pc, fma(z, -0.5, 1.0));
-  double s0 = (k & 1) ? cr : sr, c0 = (k & 1) ? sr : cr;
-  // sign flips on the high word: s negated in quadrants 2,3; c negated in quadrants 1,2
-  s0 = __hiloint2double(__double2hiint(s0) ^ ((k & 2) << 30), __double2loint(s0));
-  c0 = __hiloint2double(__double2hiint(c0) ^ (((k + 1) & 2) << 30), __double2loint(c0));
-  *sp = s0;
-  *cp = c0;
+HB_DEV void hb_tab_init(double2* tab) {   // kernels are always launched with HB_BLOCK threads (compile-time stride)
+#pragma unroll
+  for (int t = threadIdx.x; t < 128; t += HB_BLOCK) tab[t] = hb_kSinCosTab[t];
+  __syncthreads();
 }
-HB_DEV double hb_sin(double x) { double s, c; hb_sincos(x, &s, &c); return s; }
-HB_DEV double hb_cos(double x) { double s, c; hb_sincos(x, &s, &c); return c; }
 
-// hb_rcp: 1/d for the LDL^T pivots.  MUFU.RCP64H seed + two Newton steps (<= 1 ulp); no
+template <bool FAST>
+HB_DEV void hb_sincos(HbCtx& cx, double x, double* sp, double* cp) {
+  if constexpr (!FAST) {
+    sincos(x, sp, cp);
+  } else {
+    cx.oob |= (unsigned)((__double2hiint(x) & 0x7fffffff) >= 0x40F86A00);   // |x| >= 1e5, inf or nan (integer pipe)
+    const double t = fma(x, hb_kSC[0], hb_kSC[1]);
+    const double2 sc = cx.tab[__double2loint(t) & 127];
+    const double kf = t - hb_kSC[1];
+    double r = fma(-kf, hb_kSC[2], x);
+    r = fma(-kf, hb_kSC[3], r);
+    const double z = r * r;
+    double ps = fma(z, hb_kSC[6], hb_kSC[5]);
+    double pc = fma(z, hb_kSC[9], hb_kSC[8]);
+    ps = fma(z, ps, hb_kSC[4]);
+    pc = fma(z, pc, hb_kSC[7]);
+    const double sr = fma(z * r, ps, r);      // sin r
+    const double cm = z * pc;                 // cos r - 1
+    *sp = fma(sc.y, sr, fma(sc.x, cm, sc.x));    // sin(a + r) = sin a + (sin a (cos r - 1) + cos a sin r)
+    *cp = fma(-sc.x, sr, fma(sc.y, cm, sc.y));   // cos(a + r) = cos a + (cos a (cos r - 1) - sin a sin r)
+  }
+}
+template <bool FAST> HB_DEV double hb_sin(HbCtx& cx, double x) { double s, c; hb_sincos<FAST>(cx, x, &s, &c); return s; }
+template <bool FAST> HB_DEV double hb_cos(HbCtx& cx, double x) { double s, c; hb_sincos<FAST>(cx, x, &s, &c); return c; }
+
+// hb_rcp: 1/d for the mass-matrix pivots.  MUFU.RCP64H seed + two Newton steps (<= 1 ulp); no
 // denormal/overflow slow path: a pivot that needs one is flagged HB_FLAG_NOT_SPD / NONFINITE anyway.
 HB_DEV double hb_rcp(double d) {
   double x;
@@ -169,8 +251,7 @@ HB_DEV void hb_static_for(F&& f) {
 #define HB_IDX(name, tag) constexpr int name = decltype(tag)::value
 
 // ------------------------------------------------------------------ tiny dense algebra -----
-// Packed lower-triangular index.
-HB_DEV constexpr int hb_tri(int j, int k) { return j * (j + 1) / 2 + k; }
+HB_DEV constexpr int hb_tri(int j, int k) { return j * (j + 1) / 2 + k; }   // packed lower-triangular index
 
 // A = J^T diag(w) J, lower triangle packed, skipping structurally-zero products.
 // (reference: jmj = trj <> mm <> j, src/Numeric/Hamilton.hs:380)
@@ -190,52 +271,66 @@ HB_DEV void hb_mass(const double* wJ, const double* Jv, double* A) {
   });
 }
 
-// In-place LDL^T of a packed SPD matrix (no square roots: N reciprocals instead of N rsqrt +
-// divisions).  On exit A holds L below the diagonal and invd[j] = 1/d_j.  Replaces the
-// reference's explicit `inv jmj` (src/Numeric/Hamilton.hs:381); a non-positive pivot is the
-// analogue of hmatrix's singular-matrix exception.
+// Solve A x = b for the packed SPD mass matrix; A is destroyed.  Replaces the reference's explicit
+// `inv jmj` (src/Numeric/Hamilton.hs:381); a non-positive pivot is the analogue of hmatrix's
+// singular-matrix exception.  N = 1, 2: closed form with ONE reciprocal (shortest dependency chain);
+// N >= 3: LDL^T — no square roots, N reciprocals — then forward/diagonal/backward substitution.
+// pivot test on the integer pipe: true unless d is a positive normal number (NaN passes here and is
+// caught by the non-finite check on the result)
+HB_DEV bool hb_bad_pivot(double d) { return __double2hiint(d) < 0x00100000; }
+
 template <int N>
-HB_DEV void hb_ldlt(double* A, double* invd, int& flag) {
+HB_DEV void hb_spd_solve(double* A, const double* b, double* x, int& flag) {
+  if constexpr (N == 1) {
+    if (hb_bad_pivot(A[0])) flag |= HB_FLAG_NOT_SPD;
+    x[0] = b[0] * hb_rcp(A[0]);
+  } else if constexpr (N == 2) {
+    const double det = fma(A[0], A[2], -A[1] * A[1]);
+    if (hb_bad_pivot(A[0]) || hb_bad_pivot(det)) flag |= HB_FLAG_NOT_SPD;
+    const double id = hb_rcp(det);
+    const double n0 = fma(A[2], b[0], -A[1] * b[1]);
+    const double n1 = fma(A[0], b[1], -A[1] * b[0]);
+    x[0] = n0 * id;
+    x[1] = n1 * id;
+  } else {
+    double invd[N];
 #pragma unroll
-  for (int j = 0; j < N; j++) {
-    double v[N > 1 ? N : 1];
-    double d = A[hb_tri(j, j)];
+    for (int j = 0; j < N; j++) {
+      double v[N];
+      double d = A[hb_tri(j, j)];
 #pragma unroll
-    for (int k = 0; k < j; k++) {
-      v[k] = A[hb_tri(j, k)] * A[hb_tri(k, k)];   // L_jk d_k   (A_kk holds d_k)
-      d = fma(-A[hb_tri(j, k)], v[k], d);
+      for (int k = 0; k < j; k++) {
+        v[k] = A[hb_tri(j, k)] * A[hb_tri(k, k)];   // L_jk d_k   (A_kk holds d_k)
+        d = fma(-A[hb_tri(j, k)], v[k], d);
+      }
+      if (hb_bad_pivot(d)) flag |= HB_FLAG_NOT_SPD;
+      A[hb_tri(j, j)] = d;
+      const double id = hb_rcp(d);
+      invd[j] = id;
+#pragma unroll
+      for (int i = j + 1; i < N; i++) {
+        double t = A[hb_tri(i, j)];
+#pragma unroll
+        for (int k = 0; k < j; k++) t = fma(-A[hb_tri(i, k)], v[k], t);
+        A[hb_tri(i, j)] = t * id;
+      }
     }
-    if (!(d > 0.0)) flag |= HB_FLAG_NOT_SPD;
-    A[hb_tri(j, j)] = d;
-    const double id = hb_rcp(d);
-    invd[j] = id;
 #pragma unroll
-    for (int i = j + 1; i < N; i++) {
-      double t = A[hb_tri(i, j)];
+    for (int j = 0; j < N; j++) {
+      double t = b[j];
 #pragma unroll
-      for (int k = 0; k < j; k++) t = fma(-A[hb_tri(i, k)], v[k], t);
-      A[hb_tri(i, j)] = t * id;
+      for (int k = 0; k < j; k++) t = fma(-A[hb_tri(j, k)], x[k], t);
+      x[j] = t;
     }
-  }
-}
-// Solve (L D L^T) x = b.
-template <int N>
-HB_DEV void hb_ldlt_solve(const double* A, const double* invd, const double* b, double* x) {
 #pragma unroll
-  for (int j = 0; j < N; j++) {
-    double t = b[j];
+    for (int j = 0; j < N; j++) x[j] *= invd[j];
 #pragma unroll
-    for (int k = 0; k < j; k++) t = fma(-A[hb_tri(j, k)], x[k], t);
-    x[j] = t;
-  }
+    for (int j = N - 1; j >= 0; j--) {
+      double t = x[j];
 #pragma unroll
-  for (int j = 0; j < N; j++) x[j] *= invd[j];
-#pragma unroll
-  for (int j = N - 1; j >= 0; j--) {
-    double t = x[j];
-#pragma unroll
-    for (int k = j + 1; k < N; k++) t = fma(-A[hb_tri(k, j)], x[k], t);
-    x[j] = t;
+      for (int k = j + 1; k < N; k++) t = fma(-A[hb_tri(k, j)], x[k], t);
+      x[j] = t;
+    }
   }
 }
 
@@ -263,23 +358,22 @@ HB_DEV void hb_j_mul(const double* Je, const double* v, double* out) {
 // (dq, dp) = hamEqs(q, p)  (src/Numeric/Hamilton.hs:370-387):
 //   dq   = M^-1 p                                                   (:386)
 //   dp_j = +(p . M^-1 J^T W H_j M^-1 p) - dU/dq_j                   (:382-387, sign from -dHdq :375)
-// evaluated as  a = W J dq,  dp_j = sum_i a_i (H_j dq)_i - gU_j  — one LDL^T solve instead of the
+// evaluated as  a = W J dq,  dp_j = sum_i a_i (H_j dq)_i - gU_j  — one SPD solve instead of the
 // reference's explicit inverse and 5n mat-vecs, and H_j never materialised beyond its non-zeros.
-template <class S>
-HB_DEV void hb_ham_eqs(const double* prm, const double* w, const double* q, const double* p,
+template <class S, bool FAST>
+HB_DEV void hb_ham_eqs(HbCtx& cx, const double* prm, const double* w, const double* q, const double* p,
                        double* dq, double* dp, int& flag) {
   constexpr int N = S::N, M = S::M, NJ = S::NJ, NH = S::NH;
   double Jv[NJ > 0 ? NJ : 1], Hv[NH > 0 ? NH : 1], gU[N];
   double qq[N];
 #pragma unroll
   for (int j = 0; j < N; j++) qq[j] = q[j];
-  S::derivs(prm, qq, Jv, Hv, gU);
+  S::template derivs<FAST>(cx, prm, qq, Jv, Hv, gU);
   double wJ[NJ > 0 ? NJ : 1];
   hb_weigh<S>(w, Jv, wJ);
-  double A[N * (N + 1) / 2], invd[N];
+  double A[N * (N + 1) / 2];
   hb_mass<S>(wJ, Jv, A);
-  hb_ldlt<N>(A, invd, flag);
-  hb_ldlt_solve<N>(A, invd, p, dq);
+  hb_spd_solve<N>(A, p, dq, flag);
   double a[M];
   hb_j_mul<S>(wJ, dq, a);
 #pragma unroll
@@ -292,58 +386,56 @@ HB_DEV void hb_ham_eqs(const double* prm, const double* w, const double* q, cons
   });
 }
 // F(y) on the packed Phase vector y = [q, p]  (fromPs/toPs, src/Numeric/Hamilton.hs:457-462)
-template <class S>
-HB_DEV void hb_rhs(const double* prm, const double* w, const double* y, double* dy, int& flag) {
-  hb_ham_eqs<S>(prm, w, y, y + S::N, dy, dy + S::N, flag);
+template <class S, bool FAST>
+HB_DEV void hb_rhs(HbCtx& cx, const double* prm, const double* w, const double* y, double* dy, int& flag) {
+  hb_ham_eqs<S, FAST>(cx, prm, w, y, y + S::N, dy, dy + S::N, flag);
 }
 
 // momenta (src/Numeric/Hamilton.hs:262-269): p = J^T (W (J v))
-template <class S>
-HB_DEV void hb_momenta(const double* prm, const double* w, const double* q, const double* v, double* p) {
+template <class S, bool FAST>
+HB_DEV void hb_momenta(HbCtx& cx, const double* prm, const double* w, const double* q, const double* v, double* p) {
   constexpr int N = S::N, M = S::M, NJ = S::NJ;
   double Jv[NJ > 0 ? NJ : 1], qq[N], t[M];
 #pragma unroll
   for (int j = 0; j < N; j++) qq[j] = q[j];
-  S::jac(prm, qq, Jv);
+  S::template jac<FAST>(cx, prm, qq, Jv);
   hb_j_mul<S>(Jv, v, t);
 #pragma unroll
   for (int i = 0; i < M; i++) t[i] *= w[i];
   hb_jt_mul<S>(Jv, t, p);
 }
 // velocities (src/Numeric/Hamilton.hs:316-324): v = (J^T W J)^-1 p ; optionally also U(q)
-template <class S, bool WITH_U>
-HB_DEV void hb_velocities(const double* prm, const double* w, const double* q, const double* p, double* v,
+template <class S, bool FAST, bool WITH_U>
+HB_DEV void hb_velocities(HbCtx& cx, const double* prm, const double* w, const double* q, const double* p, double* v,
                           double& U, int& flag) {
   constexpr int N = S::N, NJ = S::NJ;
   double Jv[NJ > 0 ? NJ : 1], wJ[NJ > 0 ? NJ : 1], qq[N];
 #pragma unroll
   for (int j = 0; j < N; j++) qq[j] = q[j];
-  if constexpr (WITH_U) S::jac_pot(prm, qq, Jv, U); else S::jac(prm, qq, Jv);
+  if constexpr (WITH_U) S::template jac_pot<FAST>(cx, prm, qq, Jv, U); else S::template jac<FAST>(cx, prm, qq, Jv);
   hb_weigh<S>(w, Jv, wJ);
-  double A[N * (N + 1) / 2], invd[N];
+  double A[N * (N + 1) / 2];
   hb_mass<S>(wJ, Jv, A);
-  hb_ldlt<N>(A, invd, flag);
-  hb_ldlt_solve<N>(A, invd, p, v);
+  hb_spd_solve<N>(A, p, v, flag);
 }
 
 // ------------------------------------------------------------------------ integrators ------
 // Classical RK4 — the unit of BASELINE.json's metric (4 hamEqs evaluations per step).
-template <class S>
-HB_DEV void hb_rk4_step(const double* prm, const double* w, double (&y)[2 * S::N], double dt, int& flag) {
+template <class S, bool FAST>
+HB_DEV void hb_rk4_step(HbCtx& cx, const double* prm, const double* w, double (&y)[2 * S::N], double dt, double h6, int& flag) {
   constexpr int D = 2 * S::N;
   double k[D], yt[D], acc[D];
   const double hh = 0.5 * dt;
-  hb_rhs<S>(prm, w, y, k, flag);
+  hb_rhs<S, FAST>(cx, prm, w, y, k, flag);
 #pragma unroll
   for (int c = 0; c < D; c++) { acc[c] = k[c]; yt[c] = fma(hh, k[c], y[c]); }
-  hb_rhs<S>(prm, w, yt, k, flag);
+  hb_rhs<S, FAST>(cx, prm, w, yt, k, flag);
 #pragma unroll
   for (int c = 0; c < D; c++) { acc[c] = fma(2.0, k[c], acc[c]); yt[c] = fma(hh, k[c], y[c]); }
-  hb_rhs<S>(prm, w, yt, k, flag);
+  hb_rhs<S, FAST>(cx, prm, w, yt, k, flag);
 #pragma unroll
   for (int c = 0; c < D; c++) { acc[c] = fma(2.0, k[c], acc[c]); yt[c] = fma(dt, k[c], y[c]); }
-  hb_rhs<S>(prm, w, yt, k, flag);
-  const double h6 = dt / 6.0;
+  hb_rhs<S, FAST>(cx, prm, w, yt, k, flag);
 #pragma unroll
   for (int c = 0; c < D; c++) y[c] = fma(h6, acc[c] + k[c], y[c]);
 }
@@ -368,8 +460,8 @@ struct HbRkf45 {
 };
 
 // One rkf45_apply: y <- y + h * (5th-order increment); yerr; dydt_out = F(y_new).  k1 = dydt_in.
-template <class S>
-HB_DEV void hb_rkf45_apply(const double* prm, const double* w, double h, double (&y)[2 * S::N],
+template <class S, bool FAST>
+HB_DEV void hb_rkf45_apply(HbCtx& cx, const double* prm, const double* w, double h, double (&y)[2 * S::N],
                            const double (&k1)[2 * S::N], double (&yerr)[2 * S::N],
                            double (&dydt_out)[2 * S::N], int& flag) {
   constexpr int D = 2 * S::N;
@@ -377,31 +469,31 @@ HB_DEV void hb_rkf45_apply(const double* prm, const double* w, double h, double 
   double k2[D], k3[D], k4[D], k5[D], k6[D], yt[D];
 #pragma unroll
   for (int c = 0; c < D; c++) yt[c] = y[c] + T::ah0 * h * k1[c];
-  hb_rhs<S>(prm, w, yt, k2, flag);
+  hb_rhs<S, FAST>(cx, prm, w, yt, k2, flag);
 #pragma unroll
   for (int c = 0; c < D; c++) yt[c] = y[c] + h * (T::b30 * k1[c] + T::b31 * k2[c]);
-  hb_rhs<S>(prm, w, yt, k3, flag);
+  hb_rhs<S, FAST>(cx, prm, w, yt, k3, flag);
 #pragma unroll
   for (int c = 0; c < D; c++) yt[c] = y[c] + h * (T::b40 * k1[c] + T::b41 * k2[c] + T::b42 * k3[c]);
-  hb_rhs<S>(prm, w, yt, k4, flag);
+  hb_rhs<S, FAST>(cx, prm, w, yt, k4, flag);
 #pragma unroll
   for (int c = 0; c < D; c++) yt[c] = y[c] + h * (T::b50 * k1[c] + T::b51 * k2[c] + T::b52 * k3[c] + T::b53 * k4[c]);
-  hb_rhs<S>(prm, w, yt, k5, flag);
+  hb_rhs<S, FAST>(cx, prm, w, yt, k5, flag);
 #pragma unroll
   for (int c = 0; c < D; c++)
     yt[c] = y[c] + h * (T::b60 * k1[c] + T::b61 * k2[c] + T::b62 * k3[c] + T::b63 * k4[c] + T::b64 * k5[c]);
-  hb_rhs<S>(prm, w, yt, k6, flag);
+  hb_rhs<S, FAST>(cx, prm, w, yt, k6, flag);
 #pragma unroll
   for (int c = 0; c < D; c++) {
     const double di = T::c1 * k1[c] + T::c3 * k3[c] + T::c4 * k4[c] + T::c5 * k5[c] + T::c6 * k6[c];
     y[c] += h * di;
     yerr[c] = h * (T::e1 * k1[c] + T::e3 * k3[c] + T::e4 * k4[c] + T::e5 * k5[c] + T::e6 * k6[c]);
   }
-  hb_rhs<S>(prm, w, y, dydt_out, flag);
+  hb_rhs<S, FAST>(cx, prm, w, y, dydt_out, flag);
 }
 
 // Per-trajectory evolve state carried across output times like hmatrix-gsl's loop carries
-// `e` and `h` (count == 0  <=>  dydt_out not yet valid).
+// `e` and `h` (primed == false  <=>  e->count == 0: dydt_out not yet valid).
 template <int D>
 struct HbEvolve {
   double h;
@@ -410,8 +502,8 @@ struct HbEvolve {
 };
 
 // Integrate y from t to t1 with gsl_odeiv2_evolve_apply semantics: `while (t < t1) evolve_apply`.
-template <class S>
-HB_DEV void hb_rkf45_to(const double* prm, const double* w, double (&y)[2 * S::N], double& t, double t1,
+template <class S, bool FAST>
+HB_DEV void hb_rkf45_to(HbCtx& cx, const double* prm, const double* w, double (&y)[2 * S::N], double& t, double t1,
                         HbEvolve<2 * S::N>& e, int& flag) {
   constexpr int D = 2 * S::N;
   typedef HbRkf45 T;
@@ -423,7 +515,7 @@ HB_DEV void hb_rkf45_to(const double* prm, const double* w, double (&y)[2 * S::N
     double y0[D], k1[D], yerr[D], dout[D];
 #pragma unroll
     for (int c = 0; c < D; c++) y0[c] = y[c];
-    if (!e.primed) { hb_rhs<S>(prm, w, y, k1, flag); e.primed = true; }
+    if (!e.primed) { hb_rhs<S, FAST>(cx, prm, w, y, k1, flag); e.primed = true; }
     else {
 #pragma unroll
       for (int c = 0; c < D; c++) k1[c] = e.dydt[c];
@@ -431,7 +523,7 @@ HB_DEV void hb_rkf45_to(const double* prm, const double* w, double (&y)[2 * S::N
     bool final_step;
     for (;;) {   // try_step
       if ((dt >= 0.0 && h0 > dt) || (dt < 0.0 && h0 < dt)) { h0 = dt; final_step = true; } else final_step = false;
-      hb_rkf45_apply<S>(prm, w, h0, y, k1, yerr, dout, flag);
+      hb_rkf45_apply<S, FAST>(cx, prm, w, h0, y, k1, yerr, dout, flag);
       t = final_step ? t1 : t0 + h0;
       // std_control_hadjust, ord = 5
       const double h_old = h0;
@@ -442,7 +534,7 @@ HB_DEV void hb_rkf45_to(const double* prm, const double* w, double (&y)[2 * S::N
         const double r = fabs(yerr[c]) / fabs(D0);
         rmax = r > rmax ? r : rmax;
       }
-      bool nonfinite = !hb_finite(rmax);
+      const bool nonfinite = !hb_finite(rmax);
       if (rmax > 1.1) {
         double r = 0.9 / pow(rmax, 1.0 / 5.0);
         if (r < 0.2) r = 0.2;
@@ -472,11 +564,10 @@ HB_DEV void hb_rkf45_to(const double* prm, const double* w, double (&y)[2 * S::N
   }
 }
 
-// ------------------------------------------------------------------------ kernel bodies ----
-#define HB_FOR_TRAJ(i, a)                                                                     \
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (a).N;             \
-       i += (long long)gridDim.x * blockDim.x)
-
+// ------------------------------------------------------------------ per-trajectory bodies ----
+// Each hb_traj_* processes trajectory i completely (load -> compute -> store).  FAST=true is inlined
+// into the kernel; if any fast primitive left its domain (cx.oob) nothing is stored and the kernel
+// re-runs that one trajectory through the out-of-line FAST=false instance (HB_KERNEL_BODY below).
 template <int D>
 HB_DEV void hb_finish(const HbKArgs& a, long long i, const double (&y)[D], int flag) {
   bool ok = true;
@@ -487,146 +578,178 @@ HB_DEV void hb_finish(const HbKArgs& a, long long i, const double (&y)[D], int f
 }
 
 // stepHam iterated with the fixed RK4 stepper
-template <class S>
-HB_DEV void hb_body_step_rk4(const HbKArgs& a) {
+template <class S, bool FAST>
+HB_DEV void hb_traj_step_rk4(const HbKArgs& a, long long i, const double* yin, const double* w, HbCtx& cx) {
   constexpr int D = 2 * S::N;
-  double w[S::M];
-  S::inertia(a.prm, w);
-  HB_FOR_TRAJ(i, a) {
-    double y[D];
-    hb_load<D>(a.in, i, a.N, a.layout, y);
-    int flag = 0;
-    for (int s = 0; s < a.nsteps; s++) hb_rk4_step<S>(a.prm, w, y, a.dt, flag);
-    hb_store<D>(a.out, i, a.N, a.layout, y);
-    hb_finish<D>(a, i, y, flag);
-  }
+  double y[D];
+  hb_copy<D>(yin, y);
+  int flag = 0;
+  for (int s = 0; s < a.nsteps; s++) hb_rk4_step<S, FAST>(cx, a.prm, w, y, a.dt, a.dt6, flag);
+  if (FAST && cx.oob) return;
+  hb_store<D>(a.out, i, a.N, a.layout, y);
+  hb_finish<D>(a, i, y, flag);
 }
 // stepHam iterated with reference semantics: each step is a fresh adaptive solve over (0, dt)
-template <class S>
-HB_DEV void hb_body_step_rkf45(const HbKArgs& a) {
+template <class S, bool FAST>
+HB_DEV void hb_traj_step_rkf45(const HbKArgs& a, long long i, const double* yin, const double* w, HbCtx& cx) {
   constexpr int D = 2 * S::N;
-  double w[S::M];
-  S::inertia(a.prm, w);
-  HB_FOR_TRAJ(i, a) {
-    double y[D];
-    hb_load<D>(a.in, i, a.N, a.layout, y);
-    int flag = 0;
-    for (int s = 0; s < a.nsteps; s++) {
-      HbEvolve<D> e;
-      e.h = a.dt / 100;   // hi = (t1 - t0)/100, src/Numeric/Hamilton.hs:447
-      e.primed = false;
-      double t = 0.0;
-      hb_rkf45_to<S>(a.prm, w, y, t, a.dt, e, flag);
-    }
-    hb_store<D>(a.out, i, a.N, a.layout, y);
-    hb_finish<D>(a, i, y, flag);
+  double y[D];
+  hb_copy<D>(yin, y);
+  int flag = 0;
+  for (int s = 0; s < a.nsteps; s++) {
+    HbEvolve<D> e;
+    e.h = a.dt / 100;   // hi = (t1 - t0)/100, src/Numeric/Hamilton.hs:447
+    e.primed = false;
+    double t = 0.0;
+    hb_rkf45_to<S, FAST>(cx, a.prm, w, y, t, a.dt, e, flag);
   }
+  if (FAST && cx.oob) return;
+  hb_store<D>(a.out, i, a.N, a.layout, y);
+  hb_finish<D>(a, i, y, flag);
 }
 // evolveHam over a shared time grid; out[k] = batch at ts[k]
-template <class S, bool ADAPTIVE>
-HB_DEV void hb_body_evolve(const HbKArgs& a) {
+template <class S, bool FAST, bool ADAPTIVE>
+HB_DEV void hb_traj_evolve(const HbKArgs& a, long long i, const double* yin, const double* w, HbCtx& cx) {
   constexpr int D = 2 * S::N;
-  double w[S::M];
-  S::inertia(a.prm, w);
-  HB_FOR_TRAJ(i, a) {
-    double y[D];
-    hb_load<D>(a.in, i, a.N, a.layout, y);
-    hb_store<D>(a.out, i, a.N, a.layout, y);   // row 0 is the initial state
-    int flag = 0;
-    HbEvolve<D> e;
-    e.h = (a.ts[1] - a.ts[0]) / 100;
-    e.primed = false;
-    double t = a.ts[0];
-    for (int k = 1; k < a.s; k++) {
-      const double tk = a.ts[k];
-      if constexpr (ADAPTIVE) {
-        hb_rkf45_to<S>(a.prm, w, y, t, tk, e, flag);
-      } else {
-        const double h = (tk - t) / a.substeps;
-        for (int s = 0; s < a.substeps; s++) hb_rk4_step<S>(a.prm, w, y, h, flag);
-        t = tk;
-      }
-      hb_store<D>(a.out + (long long)k * a.N * D, i, a.N, a.layout, y);
+  double y[D];
+  hb_copy<D>(yin, y);
+  if (!FAST || !cx.oob) hb_store<D>(a.out, i, a.N, a.layout, y);   // row 0 is the initial state
+  int flag = 0;
+  HbEvolve<D> e;
+  e.h = (a.ts[1] - a.ts[0]) / 100;
+  e.primed = false;
+  double t = a.ts[0];
+  for (int k = 1; k < a.s; k++) {
+    const double tk = a.ts[k];
+    if constexpr (ADAPTIVE) {
+      hb_rkf45_to<S, FAST>(cx, a.prm, w, y, t, tk, e, flag);
+    } else {
+      const double h = (tk - t) / a.substeps;
+      const double h6 = h / 6.0;
+      for (int s = 0; s < a.substeps; s++) hb_rk4_step<S, FAST>(cx, a.prm, w, y, h, h6, flag);
+      t = tk;
     }
-    hb_finish<D>(a, i, y, flag);
+    if (FAST && cx.oob) return;   // rows written so far are rewritten by the slow retry (out never aliases in)
+    hb_store<D>(a.out + (long long)k * a.N * D, i, a.N, a.layout, y);
   }
+  hb_finish<D>(a, i, y, flag);
 }
-template <class S>
-HB_DEV void hb_body_ham_eqs(const HbKArgs& a) {
+template <class S, bool FAST>
+HB_DEV void hb_traj_evolve_rk4(const HbKArgs& a, long long i, const double* yin, const double* w, HbCtx& cx) { hb_traj_evolve<S, FAST, false>(a, i, yin, w, cx); }
+template <class S, bool FAST>
+HB_DEV void hb_traj_evolve_rkf45(const HbKArgs& a, long long i, const double* yin, const double* w, HbCtx& cx) { hb_traj_evolve<S, FAST, true>(a, i, yin, w, cx); }
+
+template <class S, bool FAST>
+HB_DEV void hb_traj_ham_eqs(const HbKArgs& a, long long i, const double* yin, const double* w, HbCtx& cx) {
   constexpr int D = 2 * S::N;
-  double w[S::M];
-  S::inertia(a.prm, w);
-  HB_FOR_TRAJ(i, a) {
-    double y[D], dy[D];
-    hb_load<D>(a.in, i, a.N, a.layout, y);
-    int flag = 0;
-    hb_rhs<S>(a.prm, w, y, dy, flag);
-    hb_store<D>(a.out, i, a.N, a.layout, dy);
-    hb_finish<D>(a, i, dy, flag);
-  }
+  double y[D], dy[D];
+  hb_copy<D>(yin, y);
+  int flag = 0;
+  hb_rhs<S, FAST>(cx, a.prm, w, y, dy, flag);
+  if (FAST && cx.oob) return;
+  hb_store<D>(a.out, i, a.N, a.layout, dy);
+  hb_finish<D>(a, i, dy, flag);
 }
-template <class S>
-HB_DEV void hb_body_to_phase(const HbKArgs& a) {   // Config [q, v] -> Phase [q, p]
+template <class S, bool FAST>
+HB_DEV void hb_traj_to_phase(const HbKArgs& a, long long i, const double* yin, const double* w, HbCtx& cx) {   // Config [q, v] -> Phase [q, p]
   constexpr int D = 2 * S::N, N = S::N;
-  double w[S::M];
-  S::inertia(a.prm, w);
-  HB_FOR_TRAJ(i, a) {
-    double c[D], y[D];
-    hb_load<D>(a.in, i, a.N, a.layout, c);
+  double c[D], y[D];
+  hb_copy<D>(yin, c);
 #pragma unroll
-    for (int j = 0; j < N; j++) y[j] = c[j];
-    hb_momenta<S>(a.prm, w, c, c + N, y + N);
-    hb_store<D>(a.out, i, a.N, a.layout, y);
-  }
+  for (int j = 0; j < N; j++) y[j] = c[j];
+  hb_momenta<S, FAST>(cx, a.prm, w, c, c + N, y + N);
+  if (FAST && cx.oob) return;
+  hb_store<D>(a.out, i, a.N, a.layout, y);
 }
-template <class S>
-HB_DEV void hb_body_from_phase(const HbKArgs& a) {   // Phase [q, p] -> Config [q, v]
+template <class S, bool FAST>
+HB_DEV void hb_traj_from_phase(const HbKArgs& a, long long i, const double* yin, const double* w, HbCtx& cx) {   // Phase [q, p] -> Config [q, v]
   constexpr int D = 2 * S::N, N = S::N;
-  double w[S::M];
-  S::inertia(a.prm, w);
-  HB_FOR_TRAJ(i, a) {
-    double y[D], c[D];
-    hb_load<D>(a.in, i, a.N, a.layout, y);
-    int flag = 0;
-    double U;
+  double y[D], c[D];
+  hb_copy<D>(yin, y);
+  int flag = 0;
+  double U;
 #pragma unroll
-    for (int j = 0; j < N; j++) c[j] = y[j];
-    hb_velocities<S, false>(a.prm, w, y, y + N, c + N, U, flag);
-    hb_store<D>(a.out, i, a.N, a.layout, c);
-    hb_finish<D>(a, i, c, flag);
-  }
+  for (int j = 0; j < N; j++) c[j] = y[j];
+  hb_velocities<S, FAST, false>(cx, a.prm, w, y, y + N, c + N, U, flag);
+  if (FAST && cx.oob) return;
+  hb_store<D>(a.out, i, a.N, a.layout, c);
+  hb_finish<D>(a, i, c, flag);
 }
 // out4[i] = (keP, pe, hamiltonian, lagrangian)
-template <class S>
-HB_DEV void hb_body_energies(const HbKArgs& a) {
+template <class S, bool FAST>
+HB_DEV void hb_traj_energies(const HbKArgs& a, long long i, const double* yin, const double* w, HbCtx& cx) {
   constexpr int D = 2 * S::N, N = S::N;
-  double w[S::M];
-  S::inertia(a.prm, w);
-  HB_FOR_TRAJ(i, a) {
-    double y[D], v[N];
-    hb_load<D>(a.in, i, a.N, a.layout, y);
-    int flag = 0;
-    double U;
-    hb_velocities<S, true>(a.prm, w, y, y + N, v, U, flag);
-    double T = 0.0;
+  double y[D], v[N];
+  hb_copy<D>(yin, y);
+  int flag = 0;
+  double U;
+  hb_velocities<S, FAST, true>(cx, a.prm, w, y, y + N, v, U, flag);
+  if (FAST && cx.oob) return;
+  double T = 0.0;
 #pragma unroll
-    for (int j = 0; j < N; j++) T = fma(v[j], y[N + j], T);
-    T *= 0.5;   // (vs <.> ps) / 2, src/Numeric/Hamilton.hs:349
-    double o[4] = {T, U, T + U, T - U};
-    hb_store<4>(a.out, i, a.N, 0, o);
-    hb_finish<4>(a, i, o, flag);
-  }
+  for (int j = 0; j < N; j++) T = fma(v[j], y[N + j], T);
+  T *= 0.5;   // (vs <.> ps) / 2, src/Numeric/Hamilton.hs:349
+  double o[4] = {T, U, T + U, T - U};
+  hb_store<4>(a.out, i, a.N, 0, o);
+  hb_finish<4>(a, i, o, flag);
 }
-template <class S>
-HB_DEV void hb_body_upos(const HbKArgs& a) {   // underlyingPos
+template <class S, bool FAST>
+HB_DEV void hb_traj_upos(const HbKArgs& a, long long i, const double* yin, const double* w, HbCtx& cx) {   // underlyingPos
   constexpr int N = S::N, M = S::M;
-  HB_FOR_TRAJ(i, a) {
-    double q[N], x[M];
-    hb_load<N>(a.in, i, a.N, a.layout, q);
-    S::pos(a.prm, q, x);
-    hb_store<M>(a.out, i, a.N, a.layout, x);
-  }
+  double q[N], x[M];
+  (void)w;
+  hb_copy<N>(yin, q);
+  S::template pos<FAST>(cx, a.prm, q, x);
+  if (FAST && cx.oob) return;
+  hb_store<M>(a.out, i, a.N, a.layout, x);
 }
+
+// Kernel body = fast path inline + out-of-line slow retry for the rare out-of-domain trajectory.
+// DIN = doubles loaded per trajectory.  The trajectory's input is requested from HBM BEFORE the
+// shared-memory table is staged, so the table's LDG->STS->barrier chain hides under the DRAM latency;
+// (the grid normally covers the batch, so the loop body runs once per thread).
+#define HB_KERNEL_BODY(NAME, DIN_EXPR)                                                                     \
+  template <class S>                                                                                       \
+  __device__ __noinline__ void hb_slow_##NAME(const HbKArgs& a, long long i) {                             \
+    constexpr int DIN = DIN_EXPR;                                                                          \
+    double w[S::M], yin[DIN];                                                                              \
+    S::inertia(a.prm, w);                                                                                  \
+    hb_load<DIN>(a.in, i, a.N, a.layout, yin);                                                             \
+    HbCtx cx;                                                                                              \
+    cx.tab = nullptr;                                                                                      \
+    cx.oob = 0;                                                                                            \
+    hb_traj_##NAME<S, false>(a, i, yin, w, cx);                                                            \
+  }                                                                                                        \
+  template <class S>                                                                                       \
+  HB_DEV void hb_body_##NAME(const HbKArgs& a) {                                                           \
+    constexpr int DIN = DIN_EXPR;                                                                          \
+    __shared__ double2 tab[128];                                                                           \
+    const long long stride = (long long)gridDim.x * blockDim.x;                                            \
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;                                        \
+    double yin[DIN];                                                                                       \
+    if (i < a.N) hb_load<DIN>(a.in, i, a.N, a.layout, yin);                                                \
+    if constexpr (S::TRIG) hb_tab_init(tab);                                                               \
+    double w[S::M];                                                                                        \
+    S::inertia(a.prm, w);                                                                                  \
+    while (i < a.N) {                                                                                      \
+      HbCtx cx;                                                                                            \
+      cx.tab = tab;                                                                                        \
+      cx.oob = 0;                                                                                          \
+      hb_traj_##NAME<S, true>(a, i, yin, w, cx);                                                           \
+      if (cx.oob) hb_slow_##NAME<S>(a, i);                                                                 \
+      i += stride;                                                                                         \
+      if (i < a.N) hb_load<DIN>(a.in, i, a.N, a.layout, yin);                                              \
+    }                                                                                                      \
+  }
+HB_KERNEL_BODY(step_rk4, 2 * S::N)
+HB_KERNEL_BODY(step_rkf45, 2 * S::N)
+HB_KERNEL_BODY(evolve_rk4, 2 * S::N)
+HB_KERNEL_BODY(evolve_rkf45, 2 * S::N)
+HB_KERNEL_BODY(ham_eqs, 2 * S::N)
+HB_KERNEL_BODY(to_phase, 2 * S::N)
+HB_KERNEL_BODY(from_phase, 2 * S::N)
+HB_KERNEL_BODY(energies, 2 * S::N)
+HB_KERNEL_BODY(upos, S::N)
 
 // Counter-based initial Phases; D = a.nsteps, lo = prm[0..D), hi = prm[D..2D)
 HB_DEV double hb_splitmix_u01(unsigned long long z) {
@@ -643,7 +766,8 @@ HB_DEV void hb_body_init_random(const HbKArgs& a) {
     long long i; int c;
     if (a.layout == 0) { i = e / D; c = (int)(e - i * D); } else { c = (int)(e / a.N); i = e - (long long)c * a.N; }
     const double u = hb_splitmix_u01(a.seed + (unsigned long long)D * (unsigned long long)(a.first + i) + (unsigned long long)c);
-    a.out[e] = a.prm[c] + (a.prm[D + c] - a.prm[c]) * u;
+    // no FMA contraction: bit-identical to the host-side generator (lo + (hi - lo) * u with two roundings)
+    a.out[e] = __dadd_rn(a.prm[c], __dmul_rn(__dsub_rn(a.prm[D + c], a.prm[c]), u));
   }
 }
 
@@ -659,19 +783,18 @@ HB_DEV void hb_body_init_random(const HbKArgs& a) {
 #define HB_K_UPOS 8
 #define HB_K_COUNT 9
 
-#ifndef HB_BLOCK
-#define HB_BLOCK 128
-#endif
-#ifndef HB_MINB_RK4
-#define HB_MINB_RK4 1   // min resident CTAs/SM requested for the RK4 kernels (register cap = 65536 / (128 * MINB))
+#ifdef HB_MINB_RK4   // optional register cap for the RK4 step kernel: 65536 / (HB_BLOCK * HB_MINB_RK4) registers/thread
+#define HB_LB_RK4 __launch_bounds__(HB_BLOCK, HB_MINB_RK4)
+#else
+#define HB_LB_RK4 __launch_bounds__(HB_BLOCK)
 #endif
 
 // Instantiates the per-system __global__ kernels with C linkage names PFX_<kind>.
 #define HB_DEFINE_KERNELS(SYS, PFX)                                                                         \
-  extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINB_RK4) PFX##_step_rk4(const __grid_constant__ HbKArgs a) { hb_body_step_rk4<SYS>(a); }      \
+  extern "C" __global__ void HB_LB_RK4 PFX##_step_rk4(const __grid_constant__ HbKArgs a) { hb_body_step_rk4<SYS>(a); }      \
   extern "C" __global__ void __launch_bounds__(HB_BLOCK) PFX##_step_rkf45(const __grid_constant__ HbKArgs a) { hb_body_step_rkf45<SYS>(a); }  \
-  extern "C" __global__ void __launch_bounds__(HB_BLOCK) PFX##_evolve_rk4(const __grid_constant__ HbKArgs a) { hb_body_evolve<SYS, false>(a); } \
-  extern "C" __global__ void __launch_bounds__(HB_BLOCK) PFX##_evolve_rkf45(const __grid_constant__ HbKArgs a) { hb_body_evolve<SYS, true>(a); } \
+  extern "C" __global__ void __launch_bounds__(HB_BLOCK) PFX##_evolve_rk4(const __grid_constant__ HbKArgs a) { hb_body_evolve_rk4<SYS>(a); } \
+  extern "C" __global__ void __launch_bounds__(HB_BLOCK) PFX##_evolve_rkf45(const __grid_constant__ HbKArgs a) { hb_body_evolve_rkf45<SYS>(a); } \
   extern "C" __global__ void __launch_bounds__(HB_BLOCK) PFX##_ham_eqs(const __grid_constant__ HbKArgs a) { hb_body_ham_eqs<SYS>(a); }        \
   extern "C" __global__ void __launch_bounds__(HB_BLOCK) PFX##_to_phase(const __grid_constant__ HbKArgs a) { hb_body_to_phase<SYS>(a); }      \
   extern "C" __global__ void __launch_bounds__(HB_BLOCK) PFX##_from_phase(const __grid_constant__ HbKArgs a) { hb_body_from_phase<SYS>(a); }  \

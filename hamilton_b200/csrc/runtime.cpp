@@ -23,7 +23,7 @@
 #define HB_MAXP 64
 struct HbKArgs {
   const double* in; double* out; int* flags; const double* ts;
-  long long N; double dt; int nsteps; int layout; int s; int substeps;
+  long long N; double dt; double dt6; int nsteps; int layout; int s; int substeps;
   unsigned long long seed; long long first;
   double prm[HB_MAXP];
 };
@@ -136,6 +136,7 @@ bool nvrtc_compile(const std::string& src, const std::string& arch, std::vector<
 struct hb_system {
   int m = 0, n = 0;
   int builtin = -1;                    // hb_builtin id or -1 (tape / JIT)
+  bool baked = false;                  // built-in with the default parameters: use the literal-specialised kernels
   std::vector<double> params;          // tape-level runtime parameters (<= HB_MAXP)
   std::string source;                  // generated Sys struct
   // JIT
@@ -147,7 +148,7 @@ struct hb_system {
 
   hb_status kernel(int kid, const void** fn) {
     if (builtin >= 0) {
-      *fn = hb_aot_kernel(builtin, kid);
+      *fn = hb_aot_kernel(builtin + (baked ? HB_SYS__COUNT : 0), kid);
       return *fn ? HB_OK : fail(HB_ERR_INVALID, "no such AOT kernel");
     }
     std::lock_guard<std::mutex> lk(mu);
@@ -173,17 +174,22 @@ namespace {
 struct Scratch {
   void* p[3] = {nullptr, nullptr, nullptr};
   size_t cap[3] = {0, 0, 0};
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;      // == streams[0]
+  cudaStream_t streams[3] = {nullptr, nullptr, nullptr};   // chunk pipeline: H2D / kernel / D2H of neighbouring chunks overlap
   int device = -1;
   hb_status get(int slot, size_t bytes, void** out) {
     int dev = 0;
     CU(cudaGetDevice(&dev));
     if (dev != device) {   // device switched on this thread: drop the old buffers
       for (int i = 0; i < 3; i++) { if (p[i]) { cudaSetDevice(device); cudaFree(p[i]); cudaSetDevice(dev); } p[i] = nullptr; cap[i] = 0; }
-      if (stream) { cudaStreamDestroy(stream); stream = nullptr; }
+      for (auto& st : streams) if (st) { cudaStreamDestroy(st); st = nullptr; }
+      stream = nullptr;
       device = dev;
     }
-    if (!stream) CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    if (!stream) {
+      for (auto& st : streams) CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+      stream = streams[0];
+    }
     if (bytes > cap[slot]) {
       if (p[slot]) CU(cudaFree(p[slot]));
       p[slot] = nullptr; cap[slot] = 0;
@@ -199,7 +205,7 @@ thread_local Scratch g_scratch;
 
 hb_status launch(const void* fn, const HbKArgs& a, long long work_items, cudaStream_t st) {
   if (work_items <= 0) return HB_OK;
-  static const int block = [] { const char* e = std::getenv("HB_LAUNCH_BLOCK"); int b = e ? std::atoi(e) : HB_BLOCK; return (b >= 32 && b <= 1024) ? b : HB_BLOCK; }();
+  const int block = HB_BLOCK;
   long long blocks = (work_items + block - 1) / block;
   if (blocks > 0x7fffffffLL) blocks = 0x7fffffffLL;
   void* args[] = {(void*)&a};
@@ -240,27 +246,41 @@ hb_status run_batch(const hb_system* sys, int kid, HbKArgs a, int64_t N, hb_mems
     if (dts) cudaFreeAsync(dts, st);
     return rc;
   }
-  // HB_MEM_HOST: stage through per-thread device scratch on a private stream and wait.
+  // HB_MEM_HOST: stage through per-thread device scratch and wait.  Large AOS batches are cut into chunks that
+  // flow through three streams, so the H2D copy of chunk k+1, the kernel of chunk k and the D2H copy of chunk k-1
+  // overlap (PCIe is full duplex; the copy engines and the SMs run concurrently).
   void *din = nullptr, *dout = nullptr, *dfl = nullptr;
   const bool inplace = (const void*)in == (const void*)out && in_bytes == out_bytes;
   if ((rc = g_scratch.get(0, in_bytes + (ts ? sizeof(double) * s : 0), &din))) return rc;
   if (inplace) dout = din; else if ((rc = g_scratch.get(1, out_bytes, &dout))) return rc;
-  cudaStream_t st = g_scratch.stream;
-  CU(cudaMemcpyAsync(din, in, in_bytes, cudaMemcpyHostToDevice, st));
+  if (flags && (rc = g_scratch.get(2, sizeof(int32_t) * N, &dfl))) return rc;
+  int64_t chunks = 1;
+  if (a.layout == HB_LAYOUT_AOS && out_batches == 1 && !ts && N >= (1 << 17)) {
+    chunks = N >> 16;                       // >= 64 Ki trajectories per chunk
+    if (chunks > 16) chunks = 16;
+  }
   if (ts) {
     double* dts = (double*)((char*)din + in_bytes);
-    CU(cudaMemcpyAsync(dts, ts, sizeof(double) * s, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(dts, ts, sizeof(double) * s, cudaMemcpyHostToDevice, g_scratch.streams[0]));
     a.ts = dts;
   }
-  if (flags) {
-    if ((rc = g_scratch.get(2, sizeof(int32_t) * N, &dfl))) return rc;
-    CU(cudaMemcpyAsync(dfl, flags, sizeof(int32_t) * N, cudaMemcpyHostToDevice, st));
+  for (int64_t c = 0; c < chunks; c++) {
+    const int64_t i0 = N * c / chunks, i1 = N * (c + 1) / chunks, n = i1 - i0;
+    cudaStream_t st = g_scratch.streams[c % 3];
+    const double* hin = in + (size_t)i0 * in_d;
+    double* hout = out + (size_t)i0 * out_d;
+    double* cin = (double*)din + (size_t)i0 * in_d;
+    double* cout = inplace ? cin : (double*)dout + (size_t)i0 * out_d;
+    CU(cudaMemcpyAsync(cin, hin, (size_t)n * in_d * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (flags) CU(cudaMemcpyAsync((int32_t*)dfl + i0, flags + i0, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+    HbKArgs ac = a;
+    ac.N = n; ac.in = cin; ac.out = cout; ac.flags = flags ? (int*)dfl + i0 : nullptr;
+    if (chunks == 1) { ac.N = N; }
+    if ((rc = launch(fn, ac, n, st))) return rc;
+    CU(cudaMemcpyAsync(hout, cout, (size_t)n * out_d * out_batches * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (flags) CU(cudaMemcpyAsync(flags + i0, (int32_t*)dfl + i0, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
   }
-  a.in = (const double*)din; a.out = (double*)dout; a.flags = (int*)dfl;
-  if ((rc = launch(fn, a, N, st))) return rc;
-  CU(cudaMemcpyAsync(out, dout, out_bytes, cudaMemcpyDeviceToHost, st));
-  if (flags) CU(cudaMemcpyAsync(flags, dfl, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
+  for (int k = 0; k < 3 && k < chunks; k++) CU(cudaStreamSynchronize(g_scratch.streams[k]));
   return HB_OK;
 }
 
@@ -301,9 +321,14 @@ hb_status hb_system_builtin(hb_builtin id, const double* params, int32_t n_param
   hb_system* s = new hb_system();
   s->m = spec.m; s->n = spec.n; s->builtin = (int)id;
   hb::builtin_params(id, params, n_params, s->params);
+  std::vector<double> dflt;
+  hb::builtin_params(id, nullptr, 0, dflt);
+  s->baked = std::getenv("HB_NO_BAKED") == nullptr && dflt == s->params;
+  if (s->baked) spec.baked_params = dflt;
+  if (hb_aot_kargs_size() != sizeof(HbKArgs)) { delete s; return fail(HB_ERR_INVALID, "internal: host/device HbKArgs layout mismatch"); }
   hb::GeneratedSystem g;
   std::string err;
-  if (hb::generate_system(spec, std::string("HbSys_") + hb::builtin_name(id), g, err)) s->source = g.source;
+  if (hb::generate_system(spec, std::string("HbSys_") + hb::builtin_name(id) + (s->baked ? "_dflt" : ""), g, err)) s->source = g.source;
   *out = s;
   return HB_OK;
 }
@@ -382,7 +407,7 @@ hb_status hb_batch_step(const hb_system* sys, hb_integrator integ, double dt, in
   if (integ != HB_INTEG_RK4 && integ != HB_INTEG_RKF45_GSL) return fail(HB_ERR_INVALID, "unknown integrator");
   if (nsteps < 0) return fail(HB_ERR_INVALID, "negative nsteps");
   if (integ == HB_INTEG_RKF45_GSL && !(dt > 0.0)) return fail(HB_ERR_INVALID, "RKF45_GSL needs dt > 0");
-  HbKArgs a; fill_params(sys, a); a.layout = layout; a.dt = dt; a.nsteps = nsteps;
+  HbKArgs a; fill_params(sys, a); a.layout = layout; a.dt = dt; a.dt6 = dt / 6.0; a.nsteps = nsteps;
   return run_batch(sys, integ == HB_INTEG_RK4 ? K_STEP_RK4 : K_STEP_RKF45, a, N, mem, y_in, 2 * sys->n, y_out, 2 * sys->n, 1, flags,
                    nullptr, 0, stream);
 }

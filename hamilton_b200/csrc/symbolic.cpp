@@ -293,7 +293,7 @@ SJet JetAlgebra::unary(int opc, const SJet& a) {
 }
 
 bool replay_tape(JetAlgebra& A, const hb_op* ops, int n_ops, const std::vector<SJet>& inputs, int n_params,
-                 std::vector<SJet>& nodes, std::string& err) {
+                 std::vector<SJet>& nodes, std::string& err, const double* bake) {
   nodes.assign((size_t)n_ops, SJet());
   auto bad = [&](int k, const char* what) { err = "tape node " + std::to_string(k) + ": " + what; return false; };
   for (int k = 0; k < n_ops; k++) {
@@ -310,7 +310,7 @@ bool replay_tape(JetAlgebra& A, const hb_op* ops, int n_ops, const std::vector<S
       case HB_OP_CONST: nodes[k] = A.constant(o.c); break;
       case HB_OP_PARAM:
         if (o.a < 0 || o.a >= n_params) return bad(k, "parameter index out of range");
-        nodes[k] = A.leaf(A.G.param(o.a));
+        nodes[k] = bake ? A.constant(bake[o.a]) : A.leaf(A.G.param(o.a));
         break;
       case HB_OP_ADD: nodes[k] = A.add(nodes[o.a], nodes[o.b]); break;
       case HB_OP_SUB: nodes[k] = A.sub(nodes[o.a], nodes[o.b]); break;

@@ -110,7 +110,8 @@ class JetAlgebra {
 
 // Replays a tape on jets.  `inputs` are the jets of the tape's inputs.  Returns false with a message
 // on a malformed tape (forward reference, bad opcode ...).
+// `bake` (optional, n_params values) turns PARAM leaves into literals so they fold like constants.
 bool replay_tape(JetAlgebra& A, const hb_op* ops, int n_ops, const std::vector<SJet>& inputs, int n_params,
-                 std::vector<SJet>& nodes, std::string& err);
+                 std::vector<SJet>& nodes, std::string& err, const double* bake = nullptr);
 
 }  // namespace hb

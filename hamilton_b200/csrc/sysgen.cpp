@@ -87,11 +87,11 @@ struct Emitter {
           if (p.first >= 0 && p.second >= 0) {
             if (!done_sc.count(n.a)) {
               done_sc.insert(n.a);
-              os << "    double t" << p.first << ", t" << p.second << "; hb_sincos(" << A() << ", &t" << p.first << ", &t"
+              os << "    double t" << p.first << ", t" << p.second << "; hb_sincos<FAST>(cx, " << A() << ", &t" << p.first << ", &t"
                  << p.second << ");\n";
             }
           } else {
-            fn1(n.op == Op::Sin ? "hb_sin" : "hb_cos");
+            os << "    const double t" << id << " = " << (n.op == Op::Sin ? "hb_sin" : "hb_cos") << "<FAST>(cx, " << A() << ");\n";
           }
           break;
         }
@@ -134,19 +134,24 @@ bool generate_system(const SystemSpec& spec, const std::string& name, GeneratedS
   for (int o : spec.f_outs) if (o < 0 || o >= (int)spec.f_ops.size()) { err = "f output index out of range"; return false; }
   if (spec.u_out < 0 || spec.u_out >= (int)spec.u_ops.size()) { err = "u output index out of range"; return false; }
 
+  const double* bake = nullptr;
+  if (!spec.baked_params.empty()) {
+    if ((int)spec.baked_params.size() != spec.n_params) { err = "baked_params must have n_params entries"; return false; }
+    bake = spec.baked_params.data();
+  }
   Graph G;
   JetAlgebra A2(G, 2), A1(G, 1);
   std::vector<SJet> qj;
   for (int j = 0; j < n; j++) qj.push_back(A2.variable(G.input(j), j));
   std::vector<SJet> fn;
-  if (!replay_tape(A2, spec.f_ops.data(), (int)spec.f_ops.size(), qj, spec.n_params, fn, err)) { err = "f: " + err; return false; }
+  if (!replay_tape(A2, spec.f_ops.data(), (int)spec.f_ops.size(), qj, spec.n_params, fn, err, bake)) { err = "f: " + err; return false; }
   std::vector<SJet> x;
   for (int i = 0; i < m; i++) x.push_back(fn[spec.f_outs[i]]);
   // U: first-order is all hamEqs needs (`grad u`, src/Numeric/Hamilton.hs:224); mkSystem' composes u . f (:254)
   std::vector<SJet> uin = spec.u_on_cartesian ? x : qj;
   for (auto& j : uin) j.h.clear();
   std::vector<SJet> un;
-  if (!replay_tape(A1, spec.u_ops.data(), (int)spec.u_ops.size(), uin, spec.n_params, un, err)) { err = "u: " + err; return false; }
+  if (!replay_tape(A1, spec.u_ops.data(), (int)spec.u_ops.size(), uin, spec.n_params, un, err, bake)) { err = "u: " + err; return false; }
   const SJet& U = un[spec.u_out];
 
   // structural non-zeros
@@ -163,6 +168,9 @@ bool generate_system(const SystemSpec& spec, const std::string& name, GeneratedS
   os << "// generated by hamilton_b200 sysgen: symbolic 2nd-order forward-mode derivatives of the user's tapes\n";
   os << "struct " << name << " {\n";
   os << "  static constexpr int M = " << m << ", N = " << n << ", NJ = " << NJ << ", NH = " << NH << ", NP = " << spec.n_params << ";\n";
+  bool trig = false;
+  for (const Node& nd : G.nodes) trig = trig || nd.op == Op::Sin || nd.op == Op::Cos;
+  os << "  static constexpr bool TRIG = " << (trig ? "true" : "false") << ";\n";
   os << table_fn("jidx", "int i, int j", "i * N + j", jidx);
   os << table_fn("jrow", "int e", "e", jrow) << table_fn("jcol", "int e", "e", jcol);
   os << table_fn("hrow", "int e", "e", hrow) << table_fn("hj", "int e", "e", hj) << table_fn("hk", "int e", "e", hk);
@@ -171,29 +179,30 @@ bool generate_system(const SystemSpec& spec, const std::string& name, GeneratedS
   for (int i = 0; i < m; i++) {
     const InertiaTerm& t = spec.inertia[i];
     if (t.is_param && (t.param < 0 || t.param >= spec.n_params)) { err = "inertia parameter index out of range"; return false; }
-    os << "    w[" << i << "] = " << (t.is_param ? "prm[" + std::to_string(t.param) + "]" : lit(t.value)) << ";\n";
+    os << "    w[" << i << "] = " << (t.is_param ? (bake ? lit(bake[t.param]) : "prm[" + std::to_string(t.param) + "]") : lit(t.value)) << ";\n";
   }
   os << "  }\n";
 
   auto jouts = [&] { std::vector<std::pair<std::string, int>> o; for (int e = 0; e < NJ; e++) o.push_back({"Jv[" + std::to_string(e) + "]", jnode[e]}); return o; };
-  const char* sig = "(const double* __restrict__ prm, const double* q";
+  const char* sig = "(HbCtx& cx, const double* __restrict__ prm, const double* q";
+  const char* dev = "  template <bool FAST> __device__ static __forceinline__ void ";
   {
     auto o = jouts();
     for (int e = 0; e < NH; e++) o.push_back({"Hv[" + std::to_string(e) + "]", hnode[e]});
     for (int j = 0; j < n; j++) { auto it = U.g.find(j); o.push_back({"gU[" + std::to_string(j) + "]", it == U.g.end() ? G.constant(0.0) : it->second}); }
     os << "  // J non-zeros, Hessian non-zeros and grad U in one pass (shared sub-expressions)\n";
-    os << "  __device__ static __forceinline__ void derivs" << sig << ", double* Jv, double* Hv, double* gU) {\n    (void)prm; (void)q; (void)Jv; (void)Hv;\n" << E.body(o) << "  }\n";
+    os << dev << "derivs" << sig << ", double* Jv, double* Hv, double* gU) {\n    (void)cx; (void)prm; (void)q; (void)Jv; (void)Hv;\n" << E.body(o) << "  }\n";
   }
-  os << "  __device__ static __forceinline__ void jac" << sig << ", double* Jv) {\n    (void)prm; (void)q; (void)Jv;\n" << E.body(jouts()) << "  }\n";
+  os << dev << "jac" << sig << ", double* Jv) {\n    (void)cx; (void)prm; (void)q; (void)Jv;\n" << E.body(jouts()) << "  }\n";
   {
     auto o = jouts();
     o.push_back({"U", U.v});
-    os << "  __device__ static __forceinline__ void jac_pot" << sig << ", double* Jv, double& U) {\n    (void)prm; (void)q; (void)Jv;\n" << E.body(o) << "  }\n";
+    os << dev << "jac_pot" << sig << ", double* Jv, double& U) {\n    (void)cx; (void)prm; (void)q; (void)Jv;\n" << E.body(o) << "  }\n";
   }
   {
     std::vector<std::pair<std::string, int>> o;
     for (int i = 0; i < m; i++) o.push_back({"x[" + std::to_string(i) + "]", x[i].v});
-    os << "  __device__ static __forceinline__ void pos" << sig << ", double* x) {\n    (void)prm; (void)q;\n" << E.body(o) << "  }\n";
+    os << dev << "pos" << sig << ", double* x) {\n    (void)cx; (void)prm; (void)q;\n" << E.body(o) << "  }\n";
   }
   os << "};\n";
 

@@ -22,6 +22,7 @@ struct SystemSpec {
   std::vector<hb_op> u_ops;           // u : R^n -> R  (or R^m -> R when u_on_cartesian)
   int u_out = 0;
   bool u_on_cartesian = false;
+  std::vector<double> baked_params;   // if n_params values are given, PARAM leaves become literals (specialised build)
 };
 
 struct GeneratedSystem {

@@ -6,9 +6,10 @@
 #define __host__
 #define __forceinline__ inline
 #define __restrict__
-static inline void hb_sincos(double x, double* s, double* c) { *s = std::sin(x); *c = std::cos(x); }
-static inline double hb_sin(double x) { return std::sin(x); }
-static inline double hb_cos(double x) { return std::cos(x); }
+struct HbCtx { int oob; };
+template <bool FAST> static inline void hb_sincos(HbCtx&, double x, double* s, double* c) { *s = std::sin(x); *c = std::cos(x); }
+template <bool FAST> static inline double hb_sin(HbCtx&, double x) { return std::sin(x); }
+template <bool FAST> static inline double hb_cos(HbCtx&, double x) { return std::cos(x); }
 using std::exp; using std::log; using std::sqrt; using std::pow; using std::fabs; using std::tan; using std::atan2;
 using std::asin; using std::acos; using std::atan; using std::sinh; using std::cosh; using std::tanh;
 using std::asinh; using std::acosh; using std::atanh;
@@ -21,10 +22,11 @@ extern "C" void eval(const double* prm, const double* q, double* J, double* H, d
   double Jv[S::NJ + 1], Hv[S::NH + 1], Jv2[S::NJ + 1], Jv3[S::NJ + 1];
   for (int i = 0; i < M * N; i++) J[i] = 0;
   for (int i = 0; i < N * M * N; i++) H[i] = 0;
-  S::derivs(prm, q, Jv, Hv, gU);
-  S::jac(prm, q, Jv2);
-  S::jac_pot(prm, q, Jv3, *U);
-  S::pos(prm, q, x);
+  HbCtx cx{0};
+  S::derivs<true>(cx, prm, q, Jv, Hv, gU);
+  S::jac<false>(cx, prm, q, Jv2);
+  S::jac_pot<true>(cx, prm, q, Jv3, *U);
+  S::pos<true>(cx, prm, q, x);
   S::inertia(prm, w);
   for (int e = 0; e < S::NJ; e++) {
     J[S::jrow(e) * N + S::jcol(e)] = Jv[e];

@@ -251,3 +251,22 @@ def test_large_batch_properties_at_full_size():
     fl = torch.zeros(N, dtype=torch.int32, device=y0.device)
     s.batch_step(y0, 0.01, 1, integ=L.RKF45_GSL, flags=fl)
     assert int(fl.sum()) == 0
+
+
+def test_out_of_domain_angles_take_the_slow_path(oracle_mod):
+    """|q| >= 1e5 leaves the fast sincos domain: those trajectories are redone out of line with libdevice math.
+    Mixed in one warp with ordinary trajectories; also in-place (y_out == y_in) so the retry must re-read intact input."""
+    g, o = systems_for("double_pendulum", oracle_mod)
+    y = random_phases("double_pendulum", 64)
+    y[3, 0] += 2.0e5; y[17, 1] -= 7.5e8; y[40, 0] = 1.0e5
+    yo, bad = o.batch_step(y, 0, 0.01, 3)
+    assert bad == 0
+    got = g.batch_step(y, 0.01, 3, integ=L.RK4)
+    assert maxerr(got, yo) < 1e-9            # sin/cos of 7.5e8 differ by ~1e-16 relative; 3 steps
+    buf = y.copy()
+    g.batch_step(buf, 0.01, 3, integ=L.RK4, out=buf)
+    assert np.array_equal(buf, got)
+    assert maxerr(g.batch_step(y, 0.01, 1, integ=L.RKF45_GSL), o.batch_step(y, 1, 0.01, 1)[0]) < 1e-9
+    assert maxerr(g.batch_ham_eqs(y), o.batch_ham_eqs(y)) < 1e-9
+    e = g.batch_energies(y)
+    assert maxerr(e[:, 2], [o.hamiltonian(r[:2], r[2:]) for r in y]) < 1e-9
