@@ -20,6 +20,7 @@ const char hb_engine_src[] = R"HBENGINE(
 //     static constexpr int jidx(i, j);  // position of J[i][j] in the packed list, -1 if J[i][j] == 0
 //     static constexpr int jrow(e), jcol(e);
 //     static constexpr int hrow(e), hj(e), hk(e);   // H entry e is d2 f_hrow / dq_hj dq_hk, hj <= hk
+//     static constexpr int NG, hgrp(e), gj(g), gk(g);  // H entries grouped by their (j, k) pair
 //     static constexpr bool TRIG;       // uses sin/cos (needs the shared-memory table)
 //     static void inertia(prm, w[M]);
 //     template <bool FAST> static void derivs(cx, prm, q, Jv[NJ], Hv[NH], gU[N]);   // everything hamEqs needs
@@ -118,7 +119,7 @@ HB_DEV void hb_copy(const double* src, double (&dst)[D]) {
 // trajectory on the out-of-line slow path (FAST=false: libdevice sincos with Payne-Hanek reduction).
 // Max abs error of the fast path ~2e-16 (checked against long double on the host).
 struct HbCtx {
-  const double2* tab;   // shared-memory copy of hb_kSinCosTab (fast path only)
+  unsigned tab_s;       // shared-window address of the staged hb_kSinCosTab (fast path only)
   unsigned oob;         // set when a fast-path primitive saw an argument outside its domain
 };
 
@@ -209,7 +210,8 @@ HB_DEV void hb_sincos(HbCtx& cx, double x, double* sp, double* cp) {
   } else {
     cx.oob |= (unsigned)((__double2hiint(x) & 0x7fffffff) >= 0x40F86A00);   // |x| >= 1e5, inf or nan (integer pipe)
     const double t = fma(x, hb_kSC[0], hb_kSC[1]);
-    const double2 sc = cx.tab[__double2loint(t) & 127];
+    double2 sc;   // one LDS.128 with a 32-bit shared address (no generic->shared conversion in the loop)
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(sc.x), "=d"(sc.y) : "r"(cx.tab_s + ((__double2loint(t) & 127) << 4)));
     const double kf = t - hb_kSC[1];
     double r = fma(-kf, hb_kSC[2], x);
     r = fma(-kf, hb_kSC[3], r);
@@ -237,6 +239,20 @@ HB_DEV double hb_rcp(double d) {
   e = fma(-d, x, 1.0);
   x = fma(x, e, x);
   return x;
+}
+
+// hb_recip<FAST>: the `recip` / `/` of user tapes (e.g. the two-body potential -m1 m2 / r).  Fast path = hb_rcp for
+// arguments whose exponent keeps the Newton iteration in range (2^-1000 < |x| < 2^1000); anything else (zero,
+// denormal, huge, inf, nan) is redone on the IEEE-exact slow path.
+template <bool FAST>
+HB_DEV double hb_recip(HbCtx& cx, double x) {
+  if constexpr (!FAST) {
+    return 1.0 / x;
+  } else {
+    const unsigned e = ((unsigned)__double2hiint(x) >> 20) & 0x7ff;
+    cx.oob |= (unsigned)(e - 23u > 2000u);   // biased exponent outside [23, 2023]
+    return hb_rcp(x);
+  }
 }
 
 // Compile-time loop: f(HbIdx<B>{}), ..., f(HbIdx<E-1>{}).  The Sys index tables are queried with
@@ -378,11 +394,16 @@ HB_DEV void hb_ham_eqs(HbCtx& cx, const double* prm, const double* w, const doub
   hb_j_mul<S>(wJ, dq, a);
 #pragma unroll
   for (int j = 0; j < N; j++) dp[j] = -gU[j];
-  hb_static_for<0, NH>([&](auto et) {
-    HB_IDX(e, et);
-    const double t = a[S::hrow(e)] * Hv[e];
-    dp[S::hj(e)] = fma(t, dq[S::hk(e)], dp[S::hj(e)]);
-    if constexpr (S::hj(e) != S::hk(e)) dp[S::hk(e)] = fma(t, dq[S::hj(e)], dp[S::hk(e)]);
+  // s_g = sum_i a_i H_i,(j,k) over the entries of group g = (j, k); then dp_j += s_g v_k (and dp_k += s_g v_j)
+  constexpr int NG = S::NG;
+  double sg[NG > 0 ? NG : 1];
+#pragma unroll
+  for (int g = 0; g < NG; g++) sg[g] = 0.0;
+  hb_static_for<0, NH>([&](auto et) { HB_IDX(e, et); sg[S::hgrp(e)] = fma(a[S::hrow(e)], Hv[e], sg[S::hgrp(e)]); });
+  hb_static_for<0, NG>([&](auto gt) {
+    HB_IDX(g, gt);
+    dp[S::gj(g)] = fma(sg[g], dq[S::gk(g)], dp[S::gj(g)]);
+    if constexpr (S::gj(g) != S::gk(g)) dp[S::gk(g)] = fma(sg[g], dq[S::gj(g)], dp[S::gk(g)]);
   });
 }
 // F(y) on the packed Phase vector y = [q, p]  (fromPs/toPs, src/Numeric/Hamilton.hs:457-462)
@@ -707,7 +728,7 @@ HB_DEV void hb_traj_upos(const HbKArgs& a, long long i, const double* yin, const
 // Kernel body = fast path inline + out-of-line slow retry for the rare out-of-domain trajectory.
 // DIN = doubles loaded per trajectory.  The trajectory's input is requested from HBM BEFORE the
 // shared-memory table is staged, so the table's LDG->STS->barrier chain hides under the DRAM latency;
-// (the grid normally covers the batch, so the loop body runs once per thread).
+// when a thread owns several trajectories (grid-stride), the next input is prefetched under the current compute.
 #define HB_KERNEL_BODY(NAME, DIN_EXPR)                                                                     \
   template <class S>                                                                                       \
   __device__ __noinline__ void hb_slow_##NAME(const HbKArgs& a, long long i) {                             \
@@ -716,7 +737,7 @@ HB_DEV void hb_traj_upos(const HbKArgs& a, long long i, const double* yin, const
     S::inertia(a.prm, w);                                                                                  \
     hb_load<DIN>(a.in, i, a.N, a.layout, yin);                                                             \
     HbCtx cx;                                                                                              \
-    cx.tab = nullptr;                                                                                      \
+    cx.tab_s = 0;                                                                                          \
     cx.oob = 0;                                                                                            \
     hb_traj_##NAME<S, false>(a, i, yin, w, cx);                                                            \
   }                                                                                                        \
@@ -731,14 +752,22 @@ HB_DEV void hb_traj_upos(const HbKArgs& a, long long i, const double* yin, const
     if constexpr (S::TRIG) hb_tab_init(tab);                                                               \
     double w[S::M];                                                                                        \
     S::inertia(a.prm, w);                                                                                  \
+    const unsigned tab_s = (unsigned)__cvta_generic_to_shared(tab);                                        \
     while (i < a.N) {                                                                                      \
       HbCtx cx;                                                                                            \
-      cx.tab = tab;                                                                                        \
+      cx.tab_s = tab_s;                                                                                    \
       cx.oob = 0;                                                                                          \
-      hb_traj_##NAME<S, true>(a, i, yin, w, cx);                                                           \
+      if constexpr (DIN <= 8) {   /* small state: prefetch the thread's next trajectory under this one's compute */ \
+        double ycur[DIN];                                                                                  \
+        hb_copy<DIN>(yin, ycur);                                                                           \
+        if (i + stride < a.N) hb_load<DIN>(a.in, i + stride, a.N, a.layout, yin);                          \
+        hb_traj_##NAME<S, true>(a, i, ycur, w, cx);                                                        \
+      } else {                                                                                             \
+        hb_traj_##NAME<S, true>(a, i, yin, w, cx);                                                         \
+      }                                                                                                    \
       if (cx.oob) hb_slow_##NAME<S>(a, i);                                                                 \
       i += stride;                                                                                         \
-      if (i < a.N) hb_load<DIN>(a.in, i, a.N, a.layout, yin);                                              \
+      if constexpr (DIN > 8) { if (i < a.N) hb_load<DIN>(a.in, i, a.N, a.layout, yin); }                   \
     }                                                                                                      \
   }
 HB_KERNEL_BODY(step_rk4, 2 * S::N)

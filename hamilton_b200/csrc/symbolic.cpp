@@ -29,6 +29,7 @@ int Graph::add(int a, int b) {
   if (is_zero(b)) return a;
   if (nodes[b].op == Op::Neg) return sub(a, nodes[b].a);
   if (nodes[a].op == Op::Neg) return sub(b, nodes[a].a);
+  if (a == b) return mul(constant(2.0), a);   // x + x -> 2 x (merges with neighbouring constant factors)
   if (a > b) std::swap(a, b);
   return intern({Op::Add, a, b, 0.0});
 }

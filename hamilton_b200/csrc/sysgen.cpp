@@ -74,7 +74,7 @@ struct Emitter {
         case Op::Sub: os << "    const double t" << id << " = " << A() << " - " << B() << ";\n"; break;
         case Op::Mul: os << "    const double t" << id << " = " << A() << " * " << B() << ";\n"; break;
         case Op::Neg: os << "    const double t" << id << " = -" << A() << ";\n"; break;
-        case Op::Recip: os << "    const double t" << id << " = 1.0 / " << A() << ";\n"; break;
+        case Op::Recip: os << "    const double t" << id << " = hb_recip<FAST>(cx, " << A() << ");\n"; break;
         case Op::Abs: fn1("fabs"); break;
         case Op::Signum:
           os << "    const double t" << id << " = (double)((" << A() << " > 0.0) - (" << A() << " < 0.0));\n";
@@ -162,18 +162,31 @@ bool generate_system(const SystemSpec& spec, const std::string& name, GeneratedS
   for (int i = 0; i < m; i++)
     for (auto& kv : x[i].h) { hrow.push_back(i); hj.push_back(kv.first.first); hk.push_back(kv.first.second); hnode.push_back(kv.second); }
   const int NJ = (int)jrow.size(), NH = (int)hrow.size();
+  // Hessian entries grouped by their (j, k) pair: dp_j gets (sum_i a_i H_i,jk) * v_k, one multiply per group
+  std::vector<int> hgrp(NH, 0), gj, gk;
+  {
+    std::map<std::pair<int, int>, int> gid;
+    for (int e = 0; e < NH; e++) {
+      auto key = std::make_pair(hj[e], hk[e]);
+      auto it = gid.find(key);
+      if (it == gid.end()) { it = gid.emplace(key, (int)gj.size()).first; gj.push_back(hj[e]); gk.push_back(hk[e]); }
+      hgrp[e] = it->second;
+    }
+  }
+  const int NG = (int)gj.size();
 
   Emitter E(G);
   std::ostringstream os;
   os << "// generated by hamilton_b200 sysgen: symbolic 2nd-order forward-mode derivatives of the user's tapes\n";
   os << "struct " << name << " {\n";
-  os << "  static constexpr int M = " << m << ", N = " << n << ", NJ = " << NJ << ", NH = " << NH << ", NP = " << spec.n_params << ";\n";
+  os << "  static constexpr int M = " << m << ", N = " << n << ", NJ = " << NJ << ", NH = " << NH << ", NG = " << NG << ", NP = " << spec.n_params << ";\n";
   bool trig = false;
   for (const Node& nd : G.nodes) trig = trig || nd.op == Op::Sin || nd.op == Op::Cos;
   os << "  static constexpr bool TRIG = " << (trig ? "true" : "false") << ";\n";
   os << table_fn("jidx", "int i, int j", "i * N + j", jidx);
   os << table_fn("jrow", "int e", "e", jrow) << table_fn("jcol", "int e", "e", jcol);
   os << table_fn("hrow", "int e", "e", hrow) << table_fn("hj", "int e", "e", hj) << table_fn("hk", "int e", "e", hk);
+  os << table_fn("hgrp", "int e", "e", hgrp) << table_fn("gj", "int g", "g", gj) << table_fn("gk", "int g", "g", gk);
 
   os << "  __device__ static __forceinline__ void inertia(const double* __restrict__ prm, double* w) {\n    (void)prm;\n";
   for (int i = 0; i < m; i++) {
