@@ -31,6 +31,7 @@ enum { K_STEP_RK4 = 0, K_STEP_RKF45, K_EVOLVE_RK4, K_EVOLVE_RKF45, K_HAM_EQS, K_
 static const char* const KERNEL_KINDS[K_COUNT] = {"step_rk4", "step_rkf45", "evolve_rk4", "evolve_rkf45", "ham_eqs",
                                                   "to_phase", "from_phase", "energies", "upos"};
 #define HB_BLOCK 128
+#define HB_BLOCK_OF(NCOORD) ((NCOORD) >= 8 ? 64 : 128)   // must match engine/hb_engine.cuh
 
 // from aot_kernels.cu
 extern "C" const void* hb_aot_kernel(int builtin, int kernel_id);
@@ -139,12 +140,15 @@ struct hb_system {
   bool baked = false;                  // built-in with the default parameters: use the literal-specialised kernels
   std::vector<double> params;          // tape-level runtime parameters (<= HB_MAXP)
   std::string source;                  // generated Sys struct
-  // JIT
-  std::vector<char> cubin;
-  cudaLibrary_t lib = nullptr;
+  // JIT: small systems compile all kernels in one NVRTC program at creation (cubins[K_COUNT] shared slot 0);
+  // large ones compile each kernel on first use (a 12-coordinate chain takes ~10 s per kernel).
+  hb::GeneratedSystem gen;
+  std::string arch;
+  bool lazy = false, no_code = false;
+  std::vector<char> cubins[K_COUNT];
+  cudaLibrary_t libs[K_COUNT] = {nullptr};
   const void* jit_kernels[K_COUNT] = {nullptr};
   std::mutex mu;
-  bool loaded = false;
 
   hb_status kernel(int kid, const void** fn) {
     if (builtin >= 0) {
@@ -152,16 +156,18 @@ struct hb_system {
       return *fn ? HB_OK : fail(HB_ERR_INVALID, "no such AOT kernel");
     }
     std::lock_guard<std::mutex> lk(mu);
-    if (cubin.empty()) return fail(HB_ERR_COMPILE, "system was created with HB_JIT_SKIP_COMPILE: no device code");
-    if (!loaded) {
-      CU(cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
-      for (int k = 0; k < K_COUNT; k++) {
-        cudaKernel_t kh;
-        std::string nm = std::string("hbk_") + KERNEL_KINDS[k];
-        CU(cudaLibraryGetKernel(&kh, lib, nm.c_str()));
-        jit_kernels[k] = (const void*)kh;
+    if (no_code) return fail(HB_ERR_COMPILE, "system was created with HB_JIT_SKIP_COMPILE: no device code");
+    if (!jit_kernels[kid]) {
+      const int slot = lazy ? kid : 0;
+      if (cubins[slot].empty()) {   // lazy: compile just this kernel now
+        std::string log;
+        if (!nvrtc_compile(hb::jit_translation_unit(gen, "hbk", KERNEL_KINDS[kid]), arch, cubins[slot], log)) return fail(HB_ERR_COMPILE, log);
       }
-      loaded = true;
+      if (!libs[slot]) CU(cudaLibraryLoadData(&libs[slot], cubins[slot].data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+      cudaKernel_t kh;
+      std::string nm = std::string("hbk_") + KERNEL_KINDS[kid];
+      CU(cudaLibraryGetKernel(&kh, libs[slot], nm.c_str()));
+      jit_kernels[kid] = (const void*)kh;
     }
     *fn = jit_kernels[kid];
     return HB_OK;
@@ -203,9 +209,8 @@ struct Scratch {
 };
 thread_local Scratch g_scratch;
 
-hb_status launch(const void* fn, const HbKArgs& a, long long work_items, cudaStream_t st) {
+hb_status launch(const void* fn, const HbKArgs& a, long long work_items, cudaStream_t st, int block = HB_BLOCK) {
   if (work_items <= 0) return HB_OK;
-  const int block = HB_BLOCK;
   // trajectories per thread (grid-stride with prefetch); tuning knob, default 1
   // Trajectories per thread: with >= 2 the kernel's grid-stride loop prefetches the next Phase under the current
   // step's arithmetic (measured +3..8 % on 1-step launches); only when the batch still fills the chip many times over.
@@ -247,7 +252,7 @@ hb_status run_batch(const hb_system* sys, int kid, HbKArgs a, int64_t N, hb_mems
       CU(cudaMemcpyAsync(dts, ts, sizeof(double) * s, cudaMemcpyHostToDevice, st));   // ts is tiny; pageable copy is staged by the driver
       a.ts = dts;
     }
-    rc = launch(fn, a, N, st);
+    rc = launch(fn, a, N, st, HB_BLOCK_OF(sys->n));
     if (dts) cudaFreeAsync(dts, st);
     return rc;
   }
@@ -281,7 +286,7 @@ hb_status run_batch(const hb_system* sys, int kid, HbKArgs a, int64_t N, hb_mems
     HbKArgs ac = a;
     ac.N = n; ac.in = cin; ac.out = cout; ac.flags = flags ? (int*)dfl + i0 : nullptr;
     if (chunks == 1) { ac.N = N; }
-    if ((rc = launch(fn, ac, n, st))) return rc;
+    if ((rc = launch(fn, ac, n, st, HB_BLOCK_OF(sys->n)))) return rc;
     CU(cudaMemcpyAsync(hout, cout, (size_t)n * out_d * out_batches * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (flags) CU(cudaMemcpyAsync(flags + i0, (int32_t*)dfl + i0, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
   }
@@ -358,23 +363,26 @@ hb_status hb_system_from_tape(int32_t m, int32_t n, const double* inertia, const
   hb::GeneratedSystem g;
   std::string err;
   if (!hb::generate_system(spec, "HbSysJit", g, err)) return fail(HB_ERR_TAPE, err);
-  std::string tu = hb::jit_translation_unit(g, "hbk");
-  std::vector<char> cubin;
-  std::string log;
-  const bool skip = std::getenv("HB_JIT_SKIP_COMPILE") != nullptr;   // diagnostics: symbolic stage only, system cannot launch
-  if (!skip && !nvrtc_compile(tu, jit_arch(), cubin, log)) return fail(HB_ERR_COMPILE, log);
   hb_system* s = new hb_system();
   s->m = m; s->n = n; s->builtin = -1;
   s->params.assign(params, params + n_params);
   s->source = g.source;
-  s->cubin.swap(cubin);
+  s->gen = g;
+  s->arch = jit_arch();
+  s->no_code = std::getenv("HB_JIT_SKIP_COMPILE") != nullptr;   // diagnostics: symbolic stage only, system cannot launch
+  const char* lz = std::getenv("HB_JIT_LAZY");
+  s->lazy = lz ? std::atoi(lz) != 0 : (g.nj + g.nh > 64);
+  if (!s->no_code && !s->lazy) {
+    std::string log;
+    if (!nvrtc_compile(hb::jit_translation_unit(g, "hbk"), s->arch, s->cubins[0], log)) { delete s; return fail(HB_ERR_COMPILE, log); }
+  }
   *out = s;
   return HB_OK;
 }
 
 void hb_system_free(hb_system* sys) {
   if (!sys) return;
-  if (sys->lib) cudaLibraryUnload(sys->lib);
+  for (auto& l : sys->libs) if (l) cudaLibraryUnload(l);
   delete sys;
 }
 hb_status hb_system_dims(const hb_system* sys, int32_t* m, int32_t* n) {

@@ -226,8 +226,9 @@ bool generate_system(const SystemSpec& spec, const std::string& name, GeneratedS
   return true;
 }
 
-std::string jit_translation_unit(const GeneratedSystem& g, const std::string& prefix) {
-  return "#include \"hb_engine.cuh\"\n" + g.source + "HB_DEFINE_KERNELS(" + g.name + ", " + prefix + ")\n";
+std::string jit_translation_unit(const GeneratedSystem& g, const std::string& prefix, const std::string& kind) {
+  const std::string macro = kind.empty() ? "HB_DEFINE_KERNELS" : "HB_DEFINE_KERNEL_" + kind;
+  return "#include \"hb_engine.cuh\"\n" + g.source + macro + "(" + g.name + ", " + prefix + ")\n";
 }
 
 }  // namespace hb

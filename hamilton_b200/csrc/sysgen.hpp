@@ -36,6 +36,7 @@ struct GeneratedSystem {
 bool generate_system(const SystemSpec& spec, const std::string& name, GeneratedSystem& out, std::string& err);
 
 // Full NVRTC translation unit for one system: engine include + struct + HB_DEFINE_KERNELS(name, prefix).
-std::string jit_translation_unit(const GeneratedSystem& g, const std::string& prefix);
+// `kind` empty: all nine kernels; else only that one (lazy JIT of large systems).
+std::string jit_translation_unit(const GeneratedSystem& g, const std::string& prefix, const std::string& kind = "");
 
 }  // namespace hb

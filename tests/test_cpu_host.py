@@ -216,3 +216,26 @@ def test_bench_reference_arm_runs_on_cpu():
     import json
     j = json.loads(out.strip().splitlines()[-1])
     assert j["impl"] == "reference" and j["value"] > 0 and j["cpu_baseline"]["kind"] == "port" and j["unit"] == "steps/s"
+
+
+@pytest.mark.parametrize("m,n,seed", [(2, 1, 1), (3, 2, 2), (4, 3, 3), (6, 4, 4), (5, 5, 5)])
+def test_system_compiler_on_random_user_maps(m, n, seed, oracle_mod):
+    """Arbitrary user maps (sin/exp/sqrt/recip/tanh/log/atan/powers): symbolic derivatives vs the oracle's dense jets."""
+    from tests.common import tape_args
+    from tests.test_gpu_parity import _random_system
+    rng = np.random.default_rng(100 + seed)
+    w, f, u, _ = _random_system(rng, m, n)
+    os.environ["HB_JIT_SKIP_COMPILE"] = "1"
+    try:
+        g = hb.mkSystem(w, f, u, n=n)
+    finally:
+        del os.environ["HB_JIT_SKIP_COMPILE"]
+    mm, nn, ww, fo, fouts, uo, uout, cart = tape_args(g)
+    o = oracle_mod.OracleSystem.from_tape(mm, nn, ww, fo, fouts, uo, uout, cart)
+    with tempfile.TemporaryDirectory() as tmp:
+        ev, _ = _host_eval(g, "rand%d" % seed, tmp)
+        for _ in range(6):
+            q = rng.uniform(-0.8, 0.8, size=n)
+            J, H, gU, x, U, wv = ev(q)
+            assert maxerr(J, o.jacobian(q)) < 1e-13 and maxerr(H, o.hessian(q)) < 1e-13
+            assert maxerr(gU, o.potential_grad(q)) < 1e-13 and abs(U - o.pe(q)) < 1e-13 and maxerr(wv, w) == 0

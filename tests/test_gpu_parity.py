@@ -270,3 +270,61 @@ def test_out_of_domain_angles_take_the_slow_path(oracle_mod):
     assert maxerr(g.batch_ham_eqs(y), o.batch_ham_eqs(y)) < 1e-9
     e = g.batch_energies(y)
     assert maxerr(e[:, 2], [o.hamiltonian(r[:2], r[2:]) for r in y]) < 1e-9
+
+
+def _random_system(rng, m, n):
+    """A random smooth coordinate map f: R^n -> R^m with full column rank near the origin and a random potential,
+    written against hamilton_b200.num like a user would write mkSystem's arguments."""
+    from hamilton_b200 import num
+    A = rng.normal(size=(m, n)) * 0.4
+    for j in range(n):
+        A[j, j] += 1.5                                   # f_j = 1.5 q_j + ... : J^T W J is SPD in the sampling box
+    B, Cc = rng.normal(size=(m, n)) * 0.3, rng.normal(size=(m, n))
+    E = rng.normal(size=(m,)) * 0.2
+    w = rng.uniform(0.5, 2.0, size=m)
+    ku = rng.normal(size=(n,))
+    pick = rng.integers(0, 4, size=m)
+
+    def f(q):
+        out = []
+        for i in range(m):
+            acc = 0.0
+            for j in range(n):
+                acc = acc + A[i, j] * q[j] + B[i, j] * num.sin(q[j] + Cc[i, j])
+            if pick[i] == 0:
+                acc = acc + E[i] * q[0] * q[n - 1]
+            elif pick[i] == 1:
+                acc = acc + E[i] * num.exp(0.3 * q[i % n])
+            elif pick[i] == 2:
+                acc = acc + E[i] * num.sqrt(2.0 + q[i % n] ** 2)
+            else:
+                acc = acc + E[i] / (2.0 + num.cos(q[i % n]))
+            out.append(acc)
+        return out
+
+    def u(q):
+        acc = 0.0
+        for j in range(n):
+            acc = acc + ku[j] * num.cos(q[j]) + 0.1 * q[j] ** 2 + 0.05 * num.tanh(q[j]) * q[(j + 1) % n]
+        return acc + num.log(3.0 + q[0] * q[0]) + num.atan(q[n - 1]) * 0.2
+    return list(w), f, u, n
+
+
+@pytest.mark.parametrize("m,n,seed", [(2, 1, 1), (3, 2, 2), (4, 3, 3), (6, 4, 4), (5, 5, 5)])
+def test_random_tape_systems_match_oracle(m, n, seed, oracle_mod):
+    """mkSystem on arbitrary user maps: the whole chain tracer -> symbolic AD -> NVRTC -> engine against the oracle's
+    tape interpreter (dense jets + explicit inverse), for hamEqs, RK4 and reference-semantics stepHam."""
+    rng = np.random.default_rng(100 + seed)
+    w, f, u, _ = _random_system(rng, m, n)
+    g = hb.mkSystem(w, f, u, n=n)
+    mm, nn, ww, fo, fouts, uo, uout, cart = tape_args(g)
+    o = oracle_mod.OracleSystem.from_tape(mm, nn, ww, fo, fouts, uo, uout, cart)
+    y = np.c_[rng.uniform(-0.8, 0.8, size=(97, n)), rng.uniform(-1, 1, size=(97, n))]
+    fl = np.zeros(97, np.int32)
+    assert maxerr(g.batch_ham_eqs(y, flags=fl), o.batch_ham_eqs(y)) < TOL and not fl.any()
+    yo, bad = o.batch_step(y, 0, 0.01, 3)
+    assert bad == 0 and maxerr(g.batch_step(y, 0.01, 3, integ=L.RK4), yo) < 3 * TOL
+    yo, bad = o.batch_step(y, 1, 0.02, 1)
+    assert bad == 0 and maxerr(g.batch_step(y, 0.02, 1, integ=L.RKF45_GSL), yo) < TOL
+    e = g.batch_energies(y)
+    assert maxerr(e[:, 2], [o.hamiltonian(r[:n], r[n:]) for r in y]) < TOL
