@@ -39,3 +39,48 @@ extern "C" void eval(const double* prm, const double* q, double* J, double* H, d
     H[(S::hk(e) * M + S::hrow(e)) * N + S::hj(e)] = Hv[e];
   }
 }
+
+// Symbolic hamEqs (hpre -> dense SPD solve -> hpost), momenta via smass, and U via smass_pot.
+// Returns 0 when the system was compiled with the direct contraction only (SYMH == false).
+template <class T, bool ON = T::SYMH> struct SymEval {
+  static int run(const double*, const double*, const double*, double*, double*, double*, double*) { return 0; }
+};
+template <class T> struct SymEval<T, true> {
+  static int run(const double* prm, const double* q, const double* p, double* dq, double* dp, double* Aout, double* U) {
+    constexpr int N = T::N, NT = N * (N + 1) / 2;
+    double A[NT], A2[NT], A3[NT], E[T::NE + 1];
+    HbCtx cx{0};
+    T::template hpre<true>(cx, prm, q, A, E);
+    T::template smass<true>(cx, prm, q, A2);
+    T::template smass_pot<true>(cx, prm, q, A3, *U);
+    double Md[N][N], b[N];
+    for (int j = 0; j < N; j++)
+      for (int k = 0; k <= j; k++) {
+        const int t = j * (j + 1) / 2 + k;
+        Md[j][k] = Md[k][j] = (A2[t] == A[t] && A3[t] == A[t]) ? A[t] : NAN;   // the three emitters must agree
+        Aout[j * N + k] = Aout[k * N + j] = Md[j][k];
+      }
+    for (int j = 0; j < N; j++) b[j] = p[j];
+    for (int c = 0; c < N; c++) {   // Gaussian elimination with partial pivoting (test harness only)
+      int piv = c;
+      for (int r = c + 1; r < N; r++) if (std::fabs(Md[r][c]) > std::fabs(Md[piv][c])) piv = r;
+      for (int k = 0; k < N; k++) { double t = Md[c][k]; Md[c][k] = Md[piv][k]; Md[piv][k] = t; }
+      { double t = b[c]; b[c] = b[piv]; b[piv] = t; }
+      for (int r = c + 1; r < N; r++) {
+        const double f = Md[r][c] / Md[c][c];
+        for (int k = c; k < N; k++) Md[r][k] -= f * Md[c][k];
+        b[r] -= f * b[c];
+      }
+    }
+    for (int r = N - 1; r >= 0; r--) {
+      double t = b[r];
+      for (int k = r + 1; k < N; k++) t -= Md[r][k] * dq[k];
+      dq[r] = t / Md[r][r];
+    }
+    T::template hpost<true>(cx, prm, q, E, dq, dp);
+    return 1;
+  }
+};
+extern "C" int eval_symham(const double* prm, const double* q, const double* p, double* dq, double* dp, double* A, double* U) {
+  return SymEval<S>::run(prm, q, p, dq, dp, A, U);
+}

@@ -69,6 +69,16 @@ def _host_eval(system, name, tmp):
         lib.eval(prm.ctypes.data_as(dp), q.ctypes.data_as(dp), J.ctypes.data_as(dp), H.ctypes.data_as(dp), gU.ctypes.data_as(dp),
                  x.ctypes.data_as(dp), C.byref(U), w.ctypes.data_as(dp))
         return J, H, gU, x, U.value, w
+
+    def ev_sym(q, pp):
+        """symbolic hamEqs path: (dq, dp, A, U) or None when the system uses the direct contraction"""
+        q, pp = np.ascontiguousarray(q, float), np.ascontiguousarray(pp, float)
+        dq, dpp, A, U = np.zeros(n), np.zeros(n), np.zeros((n, n)), C.c_double()
+        lib.eval_symham.restype = C.c_int
+        ok = lib.eval_symham(prm.ctypes.data_as(dp), q.ctypes.data_as(dp), pp.ctypes.data_as(dp), dq.ctypes.data_as(dp),
+                             dpp.ctypes.data_as(dp), A.ctypes.data_as(dp), C.byref(U))
+        return (dq, dpp, A, U.value) if ok else None
+    ev.sym = ev_sym
     return ev, (d[2], d[3])
 
 
@@ -96,6 +106,20 @@ def test_system_compiler_output_matches_oracle_derivatives(name, kind, oracle_mo
             assert maxerr(H, o.hessian(q)) < 1e-13
             assert maxerr(gU, o.potential_grad(q)) < 1e-13
             assert maxerr(x, o.underlying_pos(q)) < 1e-13 and abs(U - o.pe(q)) < 1e-13 * (1 + abs(U))
+            # symbolic hamEqs (csrc/polyform.cpp): mass matrix, potential and (dq, dp) against the oracle's literal
+            # restatement of src/Numeric/Hamilton.hs:370-387
+            sym = ev.sym(q, r[o.n:])
+            if name != "bezier" or kind == "jit":
+                assert sym is not None, "expected the symbolic form to be selected"
+            if sym is not None:
+                dq, dpp, A, Us = sym
+                Jo, wo = o.jacobian(q), w
+                Mo = Jo.T @ (wo[:, None] * Jo)
+                wdq, wdp = o.ham_eqs(q, r[o.n:])
+                assert maxerr(A, Mo) < 1e-13 * (1 + np.abs(Mo).max())
+                assert abs(Us - o.pe(q)) < 1e-13 * (1 + abs(Us))
+                scale = 1 + max(np.abs(wdq).max(), np.abs(wdp).max())
+                assert maxerr(dq, wdq) < 1e-12 * scale and maxerr(dpp, wdp) < 1e-12 * scale
         # sparsity is structural: chain12's Hessian tensor is "diagonal" (156 of 3456 entries), its J lower-triangular
         if name == "chain12":
             assert (nj, nh) == (156, 156)
@@ -239,3 +263,44 @@ def test_system_compiler_on_random_user_maps(m, n, seed, oracle_mod):
             J, H, gU, x, U, wv = ev(q)
             assert maxerr(J, o.jacobian(q)) < 1e-13 and maxerr(H, o.hessian(q)) < 1e-13
             assert maxerr(gU, o.potential_grad(q)) < 1e-13 and abs(U - o.pe(q)) < 1e-13 and maxerr(wv, w) == 0
+
+
+@pytest.mark.parametrize("m,n,seed", [(2, 1, 1), (3, 2, 2), (4, 3, 3), (6, 4, 4), (5, 5, 5)])
+@pytest.mark.parametrize("force", ["1", None])
+def test_symbolic_ham_eqs_on_random_user_maps(m, n, seed, force, oracle_mod):
+    """The symbolic mass-matrix / force-polynomial form of hamEqs (csrc/polyform.cpp), forced on (HB_SYMH=1) and under the
+    compiler's own cost model, against the oracle's literal restatement for arbitrary user maps."""
+    from tests.common import tape_args
+    from tests.test_gpu_parity import _random_system
+    rng = np.random.default_rng(100 + seed)
+    w, f, u, _ = _random_system(rng, m, n)
+    os.environ["HB_JIT_SKIP_COMPILE"] = "1"
+    if force:
+        os.environ["HB_SYMH"] = force
+    try:
+        g = hb.mkSystem(w, f, u, n=n)
+    finally:
+        del os.environ["HB_JIT_SKIP_COMPILE"]
+        os.environ.pop("HB_SYMH", None)
+    mm, nn, ww, fo, fouts, uo, uout, cart = tape_args(g)
+    o = oracle_mod.OracleSystem.from_tape(mm, nn, ww, fo, fouts, uo, uout, cart)
+    with tempfile.TemporaryDirectory() as tmp:
+        ev, _ = _host_eval(g, "symrand%d" % seed, tmp)
+        checked = 0
+        for _ in range(6):
+            q, pp = rng.uniform(-0.8, 0.8, size=n), rng.uniform(-1, 1, size=n)
+            sym = ev.sym(q, pp)
+            if sym is None:
+                assert not force or "self-check" in g.source() or "too large" in g.source()
+                continue
+            dq, dpp, A, Us = sym
+            Jo = o.jacobian(q)
+            Mo = Jo.T @ (np.asarray(w)[:, None] * Jo)
+            wdq, wdp = o.ham_eqs(q, pp)
+            cond = np.linalg.cond(Mo)
+            assert maxerr(A, Mo) < 1e-13 * (1 + np.abs(Mo).max()) and abs(Us - o.pe(q)) < 1e-13 * (1 + abs(Us))
+            scale = (1 + max(np.abs(wdq).max(), np.abs(wdp).max())) * max(1.0, cond)
+            assert maxerr(dq, wdq) < 1e-13 * scale and maxerr(dpp, wdp) < 1e-13 * scale
+            checked += 1
+        if force:
+            assert checked > 0 or "hamEqs form: direct" in g.source()
