@@ -11,8 +11,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../include/hamilton_b200.h"
@@ -32,6 +34,7 @@ static const char* const KERNEL_KINDS[K_COUNT] = {"step_rk4", "step_rkf45", "evo
                                                   "to_phase", "from_phase", "energies", "upos"};
 #define HB_BLOCK 128
 #define HB_BLOCK_OF(NCOORD) ((NCOORD) >= 8 ? 64 : 128)   // must match engine/hb_engine.cuh
+#define HB_MAXBLOCK_OF(NCOORD) HB_BLOCK_OF(NCOORD)
 
 // from aot_kernels.cu
 extern "C" const void* hb_aot_kernel(int builtin, int kernel_id);
@@ -209,17 +212,52 @@ struct Scratch {
 };
 thread_local Scratch g_scratch;
 
-hb_status launch(const void* fn, const HbKArgs& a, long long work_items, cudaStream_t st, int block = HB_BLOCK) {
+// Resident CTA slots of a kernel on the current device (SMs x occupancy), cached per (device, function).
+int resident_ctas(const void* fn, int block) {
+  static std::mutex mu;
+  static std::map<std::tuple<int, const void*, int>, int> cache;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = cache.find(std::make_tuple(dev, fn, block));
+  if (it != cache.end()) return it->second;
+  int sms = 0, per_sm = 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, block, 0) != cudaSuccess) { cudaGetLastError(); return 0; }
+  const int slots = sms * (per_sm > 0 ? per_sm : 1);
+  cache[std::make_tuple(dev, fn, block)] = slots;
+  return slots;
+}
+
+// Launch policy.  Batches that fill the chip run as ONE resident wave (grid = SMs x occupancy, 148 x k on B200): every CTA
+// stages the sin/cos table once and walks its trajectories with a grid-stride loop that prefetches the next Phase under
+// the current step's arithmetic.  Every launch carries the programmatic-stream-serialization attribute: the kernels call
+// griddepcontrol.launch_dependents first thing and griddepcontrol.wait before their first global read, so in a stream (or
+// captured graph) of back-to-back steps the next kernel's launch latency and table staging hide under this kernel's tail.
+hb_status launch(const void* fn, const HbKArgs& a, long long work_items, cudaStream_t st, int block = HB_BLOCK, int max_block = HB_BLOCK) {
   if (work_items <= 0) return HB_OK;
-  // trajectories per thread (grid-stride with prefetch); tuning knob, default 1
-  // Trajectories per thread: with >= 2 the kernel's grid-stride loop prefetches the next Phase under the current
-  // step's arithmetic (measured +3..8 % on 1-step launches); only when the batch still fills the chip many times over.
-  static const int tpt_env = [] { const char* e = std::getenv("HB_TRAJ_PER_THREAD"); int t = e ? std::atoi(e) : 0; return (t >= 1 && t <= 64) ? t : 0; }();
-  const int tpt = tpt_env ? tpt_env : (work_items >= (1LL << 18) ? 2 : 1);
-  long long blocks = (work_items + (long long)block * tpt - 1) / ((long long)block * tpt);
+  static const int block_env = [] { const char* e = std::getenv("HB_BLOCK"); int t = e ? std::atoi(e) : 0; return (t >= 32 && t <= 1024 && t % 32 == 0) ? t : 0; }();
+  if (block_env && block_env <= max_block) block = block_env;
+  static const double waves_env = [] { const char* e = std::getenv("HB_GRID_WAVES"); double t = e ? std::atof(e) : 0.0; return (t > 0 && t <= 4096) ? t : 0.0; }();
+  static const bool pdl = std::getenv("HB_NO_PDL") == nullptr;
+  long long blocks = (work_items + block - 1) / block;
+  const int slots = resident_ctas(fn, block);
+  const long long cap = (long long)((double)slots * (waves_env > 0 ? waves_env : 2.0));
+  if (slots > 0 && blocks > cap) blocks = cap;
   if (blocks > 0x7fffffffLL) blocks = 0x7fffffffLL;
   void* args[] = {(void*)&a};
-  CU(cudaLaunchKernel(fn, dim3((unsigned)blocks), dim3(block), args, 0, st));
+  cudaLaunchConfig_t cfg;
+  std::memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3((unsigned)blocks);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  CU(cudaLaunchKernelExC(&cfg, fn, args));
   return HB_OK;
 }
 
@@ -252,7 +290,7 @@ hb_status run_batch(const hb_system* sys, int kid, HbKArgs a, int64_t N, hb_mems
       CU(cudaMemcpyAsync(dts, ts, sizeof(double) * s, cudaMemcpyHostToDevice, st));   // ts is tiny; pageable copy is staged by the driver
       a.ts = dts;
     }
-    rc = launch(fn, a, N, st, HB_BLOCK_OF(sys->n));
+    rc = launch(fn, a, N, st, HB_BLOCK_OF(sys->n), HB_MAXBLOCK_OF(sys->n));
     if (dts) cudaFreeAsync(dts, st);
     return rc;
   }
@@ -286,7 +324,7 @@ hb_status run_batch(const hb_system* sys, int kid, HbKArgs a, int64_t N, hb_mems
     HbKArgs ac = a;
     ac.N = n; ac.in = cin; ac.out = cout; ac.flags = flags ? (int*)dfl + i0 : nullptr;
     if (chunks == 1) { ac.N = N; }
-    if ((rc = launch(fn, ac, n, st, HB_BLOCK_OF(sys->n)))) return rc;
+    if ((rc = launch(fn, ac, n, st, HB_BLOCK_OF(sys->n), HB_MAXBLOCK_OF(sys->n)))) return rc;
     CU(cudaMemcpyAsync(hout, cout, (size_t)n * out_d * out_batches * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (flags) CU(cudaMemcpyAsync(flags + i0, (int32_t*)dfl + i0, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
   }

@@ -281,7 +281,11 @@ SymHam build_symham(Graph& G, const SystemSpec& spec, const std::vector<SJet>& x
     if (nd.op == Op::Const || nd.op == Op::Param) continue;
     dep[id] = (nd.a >= 0 && dep[nd.a]) || (nd.b >= 0 && dep[nd.b]);
   }
-  {
+  // Values handed from hpre to hpost.  Small systems carry every velocity-independent sub-expression (all of it is
+  // then evaluated before the solve, off the critical path).  When that set is large the live state across the solve
+  // (A + E) no longer fits the register file, so only the non-polynomial atoms (sin/cos/exp/recip ... results) are
+  // carried and hpost re-forms the polynomial coefficients from them.
+  auto cut = [&](bool atoms_only) {
     std::set<int> seen, carried;
     std::vector<int> stack(R.dp.begin(), R.dp.end());
     while (!stack.empty()) {
@@ -289,12 +293,15 @@ SymHam build_symham(Graph& G, const SystemSpec& spec, const std::vector<SJet>& x
       if (!seen.insert(id).second) continue;
       const Node& nd = G.nodes[id];
       if (nd.op == Op::Const || nd.op == Op::Input || nd.op == Op::Param) continue;
-      if (!dep[id] && nd.op != Op::Neg) { carried.insert(id); continue; }   // computed before the solve
+      const bool poly = nd.op == Op::Add || nd.op == Op::Sub || nd.op == Op::Mul || nd.op == Op::Neg;
+      if (!dep[id] && nd.op != Op::Neg && !(atoms_only && poly)) { carried.insert(id); continue; }   // computed before the solve
       if (nd.a >= 0) stack.push_back(nd.a);
       if (nd.b >= 0) stack.push_back(nd.b);
     }
     R.carried.assign(carried.begin(), carried.end());
-  }
+  };
+  cut(false);
+  if ((int)R.carried.size() + n * (n + 1) / 2 > 56) cut(true);
   // cost model: symbolic (hpre + hpost) vs the engine's direct sparse contraction
   {
     std::vector<int> roots = R.A;
