@@ -9,7 +9,7 @@ the I/O-honest mode SURVEY.md §8(d) defines (32·n = 64 algorithmic bytes per t
 
   value     steps/s with the batch resident in HBM (device pointers through the C ABI), CUDA-event timed.
   e2e       the same call through the C ABI with HOST buffers (pinned): H2D + kernel + D2H inside the timed region.
-  roofline  HBM roofline of the dominant kernel (hbk_double_pendulum_step_rk4) + the FP64-pipe view that actually binds.
+  roofline  HBM roofline of the dominant kernel (hbk_double_pendulum_dflt_step_rk4) + the FP64-pipe view that actually binds.
   cpu_baseline  the CPU oracle (restatement of the reference algorithm) timed on this box's host cores, bounded sample.
 
 `--impl reference` times the reference's CPU implementation of the path: the Haskell+GSL binary cannot be built in this
@@ -53,52 +53,86 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons during the timed region (recipe in B200_PROFILING.md)."""
+    """SM clock and throttle reasons DURING the timed region.  The region is tens of milliseconds long, so NVML is polled
+    from a thread every ~1 ms (nvidia-smi -lms cannot sample that fast); falls back to nvidia-smi when NVML is missing."""
+
+    REASONS = (("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40), ("sw_power_cap", 0x4))
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.h, self.stop_flag, self.mx = index, [], None, None, False, None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.nv = pynvml
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.h = None
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
-                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                clk = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.rows.append((time.time(), clk, mask))
+            except Exception:
+                pass
+            time.sleep(0.0005)
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append((time.time(), line.strip()))
+            f = [x.strip() for x in line.strip().split(",")]
+            try:
+                mask = sum(bit for (name, bit), v in zip((("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+                                                          ("sw_power_cap", 0x4)), f[3:7]) if v.lower().startswith("active"))
+                self.mx = float(f[1])
+                self.rows.append((time.time(), float(f[0]), mask))
+            except (ValueError, IndexError):
+                pass
 
     def stop(self, t0, t1):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.12)
-        self.proc.terminate()
-        sm, mx, reasons = [], None, set()
-        for ts, line in self.rows:
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                clk = float(f[0]); mx = float(f[1])
-            except ValueError:
-                continue
-            if t0 - 0.05 <= ts <= t1 + 0.05:
-                sm.append(clk)
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-        if not sm:   # region shorter than the sampling period: use every sample we have
-            for ts, line in self.rows:
-                try:
-                    sm.append(float(line.split(",")[0]))
-                except ValueError:
-                    pass
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        if self.h is None and not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML / nvidia-smi"], "samples": 0}
+        if self.h is None:
+            time.sleep(0.05)
+            self.proc.terminate()
+        self.stop_flag = True
+        inside = [(c, m) for ts, c, m in self.rows if t0 <= ts <= t1]
+        where = "timed region"
+        if not inside:   # region shorter than the sampling period: nearest samples around it
+            inside = [(c, m) for ts, c, m in self.rows if t0 - 0.1 <= ts <= t1 + 0.1]
+            where = "timed region +- 100 ms"
+        reasons = set()
+        for _c, m in inside:
+            for name, bit in self.REASONS:
+                if m & bit:
+                    reasons.add(name)
+        sm = [c for c, _m in inside]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.mx, "reasons": sorted(reasons), "samples": len(sm),
+                "sampled": ("NVML every ~1 ms, " if self.h is not None else "nvidia-smi -lms 20, ") + where}
 
 
 def cpu_oracle_steps_per_sec(target_seconds, threads):
@@ -305,7 +339,7 @@ def main():
             "e2e": {"value": world * N * e2e_steps / (e2e_ms * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": N * 32, "d2h_bytes_per_step": N * 32,
                     "steps": e2e_steps, "call": "hb_batch_step(HB_INTEG_RK4, nsteps=1, HB_MEM_HOST) on pinned host arrays, blocking"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "peak_source": peak_src, "kernel": "hbk_double_pendulum_step_rk4",
+                         "peak_source": peak_src, "kernel": "hbk_double_pendulum_dflt_step_rk4",
                          "algorithmic_bytes_per_launch": N * ALGO_BYTES_PER_STEP,
                          "note": "the binding resource is the FP64 pipe, not HBM (SURVEY.md §8(d)); see fp64", "fp64": fp64},
         }

@@ -33,12 +33,15 @@ enum { K_STEP_RK4 = 0, K_STEP_RKF45, K_EVOLVE_RK4, K_EVOLVE_RKF45, K_HAM_EQS, K_
 static const char* const KERNEL_KINDS[K_COUNT] = {"step_rk4", "step_rkf45", "evolve_rk4", "evolve_rkf45", "ham_eqs",
                                                   "to_phase", "from_phase", "energies", "upos"};
 #define HB_BLOCK 128
-#define HB_BLOCK_OF(NCOORD) ((NCOORD) >= 8 ? 64 : 128)   // must match engine/hb_engine.cuh
+#define HB_BLOCK_OF(NCOORD) 128   // must match engine/hb_engine.cuh
+#define HB_BIG_N 8
+#define HB_DYN_DOUBLES(NCOORD, NE_) ((NCOORD) >= HB_BIG_N ? 3 * 2 * (NCOORD) + (NE_) : 0)
 #define HB_MAXBLOCK_OF(NCOORD) HB_BLOCK_OF(NCOORD)
 
 // from aot_kernels.cu
 extern "C" const void* hb_aot_kernel(int builtin, int kernel_id);
 extern "C" const void* hb_aot_init_random(void);
+extern "C" int hb_aot_dyn_doubles(int builtin);
 extern "C" size_t hb_aot_kargs_size(void);
 // from gen/engine_embed.inc (the engine header as a string, for NVRTC)
 extern const char hb_engine_src[];
@@ -142,6 +145,7 @@ struct hb_system {
   int builtin = -1;                    // hb_builtin id or -1 (tape / JIT)
   bool baked = false;                  // built-in with the default parameters: use the literal-specialised kernels
   std::vector<double> params;          // tape-level runtime parameters (<= HB_MAXP)
+  int dyn_doubles = 0;                 // dynamic shared memory per thread (doubles) every kernel of this system is launched with
   std::string source;                  // generated Sys struct
   // JIT: small systems compile all kernels in one NVRTC program at creation (cubins[K_COUNT] shared slot 0);
   // large ones compile each kernel on first use (a 12-coordinate chain takes ~10 s per kernel).
@@ -186,12 +190,23 @@ struct Scratch {
   cudaStream_t stream = nullptr;      // == streams[0]
   cudaStream_t streams[3] = {nullptr, nullptr, nullptr};   // chunk pipeline: H2D / kernel / D2H of neighbouring chunks overlap
   int device = -1;
+  std::vector<cudaEvent_t> events;    // chunk pipeline: upload-done / kernel-done per chunk
+  hb_status need_events(int n) {
+    while ((int)events.size() < n) {
+      cudaEvent_t e;
+      CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      events.push_back(e);
+    }
+    return HB_OK;
+  }
   hb_status get(int slot, size_t bytes, void** out) {
     int dev = 0;
     CU(cudaGetDevice(&dev));
     if (dev != device) {   // device switched on this thread: drop the old buffers
       for (int i = 0; i < 3; i++) { if (p[i]) { cudaSetDevice(device); cudaFree(p[i]); cudaSetDevice(dev); } p[i] = nullptr; cap[i] = 0; }
       for (auto& st : streams) if (st) { cudaStreamDestroy(st); st = nullptr; }
+      for (auto e : events) cudaEventDestroy(e);
+      events.clear();
       stream = nullptr;
       device = dev;
     }
@@ -213,7 +228,7 @@ struct Scratch {
 thread_local Scratch g_scratch;
 
 // Resident CTA slots of a kernel on the current device (SMs x occupancy), cached per (device, function).
-int resident_ctas(const void* fn, int block) {
+int resident_ctas(const void* fn, int block, size_t dyn_smem) {
   static std::mutex mu;
   static std::map<std::tuple<int, const void*, int>, int> cache;
   int dev = 0;
@@ -222,8 +237,9 @@ int resident_ctas(const void* fn, int block) {
   auto it = cache.find(std::make_tuple(dev, fn, block));
   if (it != cache.end()) return it->second;
   int sms = 0, per_sm = 0;
+  if (dyn_smem > 48 * 1024 && cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem) != cudaSuccess) { cudaGetLastError(); return -1; }
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, block, 0) != cudaSuccess) { cudaGetLastError(); return 0; }
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, block, dyn_smem) != cudaSuccess) { cudaGetLastError(); return 0; }
   const int slots = sms * (per_sm > 0 ? per_sm : 1);
   cache[std::make_tuple(dev, fn, block)] = slots;
   return slots;
@@ -234,14 +250,17 @@ int resident_ctas(const void* fn, int block) {
 // the current step's arithmetic.  Every launch carries the programmatic-stream-serialization attribute: the kernels call
 // griddepcontrol.launch_dependents first thing and griddepcontrol.wait before their first global read, so in a stream (or
 // captured graph) of back-to-back steps the next kernel's launch latency and table staging hide under this kernel's tail.
-hb_status launch(const void* fn, const HbKArgs& a, long long work_items, cudaStream_t st, int block = HB_BLOCK, int max_block = HB_BLOCK) {
+hb_status launch(const void* fn, const HbKArgs& a, long long work_items, cudaStream_t st, int block = HB_BLOCK, int max_block = HB_BLOCK,
+                 int dyn_doubles = 0) {
   if (work_items <= 0) return HB_OK;
   static const int block_env = [] { const char* e = std::getenv("HB_BLOCK"); int t = e ? std::atoi(e) : 0; return (t >= 32 && t <= 1024 && t % 32 == 0) ? t : 0; }();
-  if (block_env && block_env <= max_block) block = block_env;
+  if (block_env && block_env <= max_block && dyn_doubles == 0) block = block_env;   // (shared-memory layouts assume HB_BLOCK_OF)
   static const double waves_env = [] { const char* e = std::getenv("HB_GRID_WAVES"); double t = e ? std::atof(e) : 0.0; return (t > 0 && t <= 4096) ? t : 0.0; }();
   static const bool pdl = std::getenv("HB_NO_PDL") == nullptr;
   long long blocks = (work_items + block - 1) / block;
-  const int slots = resident_ctas(fn, block);
+  const size_t dyn_smem = (size_t)dyn_doubles * sizeof(double) * block;
+  const int slots = resident_ctas(fn, block, dyn_smem);
+  if (slots < 0) return fail(HB_ERR_CUDA, "kernel needs more dynamic shared memory than the device offers");
   const long long cap = (long long)((double)slots * (waves_env > 0 ? waves_env : 2.0));
   if (slots > 0 && blocks > cap) blocks = cap;
   if (blocks > 0x7fffffffLL) blocks = 0x7fffffffLL;
@@ -250,7 +269,7 @@ hb_status launch(const void* fn, const HbKArgs& a, long long work_items, cudaStr
   std::memset(&cfg, 0, sizeof cfg);
   cfg.gridDim = dim3((unsigned)blocks);
   cfg.blockDim = dim3(block);
-  cfg.dynamicSmemBytes = 0;
+  cfg.dynamicSmemBytes = dyn_smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -290,9 +309,33 @@ hb_status run_batch(const hb_system* sys, int kid, HbKArgs a, int64_t N, hb_mems
       CU(cudaMemcpyAsync(dts, ts, sizeof(double) * s, cudaMemcpyHostToDevice, st));   // ts is tiny; pageable copy is staged by the driver
       a.ts = dts;
     }
-    rc = launch(fn, a, N, st, HB_BLOCK_OF(sys->n), HB_MAXBLOCK_OF(sys->n));
+    rc = launch(fn, a, N, st, HB_BLOCK_OF(sys->n), HB_MAXBLOCK_OF(sys->n), sys->dyn_doubles);
     if (dts) cudaFreeAsync(dts, st);
     return rc;
+  }
+  // HB_MEM_HOST, page-locked buffers, opt-in (HB_HOST_DIRECT=1): ONE kernel reads the Phases straight out of host memory
+  // and writes the results straight back (zero-copy).  Right for coherent CPU<->GPU links; over PCIe gen5 it measured 2x
+  // SLOWER than the staged pipeline below (4.5e8 vs 8.8e8 steps/s on config 2, profiles/r1f), so it is off by default.
+  static const bool direct_ok = [] { const char* e = std::getenv("HB_HOST_DIRECT"); return e && e[0] == '1'; }();
+  if (direct_ok) {
+    auto pinned_dev = [](const void* h, void** d) {
+      cudaPointerAttributes at;
+      if (cudaPointerGetAttributes(&at, h) != cudaSuccess) { cudaGetLastError(); return false; }
+      if (at.type != cudaMemoryTypeHost || !at.devicePointer) return false;
+      *d = at.devicePointer;
+      return true;
+    };
+    void *din_h = nullptr, *dout_h = nullptr, *dfl_h = nullptr;
+    if (pinned_dev(in, &din_h) && pinned_dev(out, &dout_h) && (!flags || pinned_dev(flags, &dfl_h))) {
+      void* dts = nullptr;
+      if ((rc = g_scratch.get(0, ts ? sizeof(double) * s : 8, &dts))) return rc;
+      cudaStream_t st = g_scratch.stream;
+      if (ts) { CU(cudaMemcpyAsync(dts, ts, sizeof(double) * s, cudaMemcpyHostToDevice, st)); a.ts = (const double*)dts; }
+      a.in = (const double*)din_h; a.out = (double*)dout_h; a.flags = (int*)dfl_h;
+      if ((rc = launch(fn, a, N, st, HB_BLOCK_OF(sys->n), HB_MAXBLOCK_OF(sys->n), sys->dyn_doubles))) return rc;
+      CU(cudaStreamSynchronize(st));
+      return HB_OK;
+    }
   }
   // HB_MEM_HOST: stage through per-thread device scratch and wait.  Large AOS batches are cut into chunks that
   // flow through three streams, so the H2D copy of chunk k+1, the kernel of chunk k and the D2H copy of chunk k-1
@@ -302,33 +345,54 @@ hb_status run_batch(const hb_system* sys, int kid, HbKArgs a, int64_t N, hb_mems
   if ((rc = g_scratch.get(0, in_bytes + (ts ? sizeof(double) * s : 0), &din))) return rc;
   if (inplace) dout = din; else if ((rc = g_scratch.get(1, out_bytes, &dout))) return rc;
   if (flags && (rc = g_scratch.get(2, sizeof(int32_t) * N, &dfl))) return rc;
+  // Three decoupled in-order queues joined by events: every H2D copy sits back to back on the upload stream, the kernel
+  // of chunk c waits only for its own upload, the D2H copy of chunk c only for its own kernel — both PCIe directions
+  // stay busy for the whole call except for one chunk of fill and one of drain.
+  static const int chunks_env = [] { const char* e = std::getenv("HB_HOST_CHUNKS"); int t = e ? std::atoi(e) : 0; return (t >= 1 && t <= 64) ? t : 0; }();
   int64_t chunks = 1;
-  if (a.layout == HB_LAYOUT_AOS && out_batches == 1 && !ts && N >= (1 << 17)) {
-    chunks = N >> 16;                       // >= 64 Ki trajectories per chunk
-    if (chunks > 16) chunks = 16;
+  if (a.layout == HB_LAYOUT_AOS && out_batches == 1 && !ts && N >= (1 << 16)) {
+    chunks = chunks_env ? chunks_env : N >> 14;     // >= 16 Ki trajectories per chunk
+    if (chunks > 32) chunks = chunks_env ? chunks_env : 32;
+    if (chunks < 1) chunks = 1;
   }
+  cudaStream_t s_up = g_scratch.streams[0], s_k = g_scratch.streams[1], s_down = g_scratch.streams[2];
+  if ((rc = g_scratch.need_events((int)(2 * chunks)))) return rc;
   if (ts) {
     double* dts = (double*)((char*)din + in_bytes);
-    CU(cudaMemcpyAsync(dts, ts, sizeof(double) * s, cudaMemcpyHostToDevice, g_scratch.streams[0]));
+    CU(cudaMemcpyAsync(dts, ts, sizeof(double) * s, cudaMemcpyHostToDevice, s_up));
     a.ts = dts;
   }
   for (int64_t c = 0; c < chunks; c++) {
     const int64_t i0 = N * c / chunks, i1 = N * (c + 1) / chunks, n = i1 - i0;
-    cudaStream_t st = g_scratch.streams[c % 3];
     const double* hin = in + (size_t)i0 * in_d;
     double* hout = out + (size_t)i0 * out_d;
     double* cin = (double*)din + (size_t)i0 * in_d;
     double* cout = inplace ? cin : (double*)dout + (size_t)i0 * out_d;
-    CU(cudaMemcpyAsync(cin, hin, (size_t)n * in_d * sizeof(double), cudaMemcpyHostToDevice, st));
-    if (flags) CU(cudaMemcpyAsync((int32_t*)dfl + i0, flags + i0, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+    cudaEvent_t up = g_scratch.events[2 * c], done = g_scratch.events[2 * c + 1];
+    if (chunks == 1) {   // whole batch (any layout, evolve output): copy everything
+      CU(cudaMemcpyAsync(din, in, in_bytes, cudaMemcpyHostToDevice, s_up));
+      if (flags) CU(cudaMemcpyAsync(dfl, flags, sizeof(int32_t) * N, cudaMemcpyHostToDevice, s_up));
+    } else {
+      CU(cudaMemcpyAsync(cin, hin, (size_t)n * in_d * sizeof(double), cudaMemcpyHostToDevice, s_up));
+      if (flags) CU(cudaMemcpyAsync((int32_t*)dfl + i0, flags + i0, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s_up));
+    }
+    CU(cudaEventRecord(up, s_up));
+    CU(cudaStreamWaitEvent(s_k, up, 0));
     HbKArgs ac = a;
-    ac.N = n; ac.in = cin; ac.out = cout; ac.flags = flags ? (int*)dfl + i0 : nullptr;
-    if (chunks == 1) { ac.N = N; }
-    if ((rc = launch(fn, ac, n, st, HB_BLOCK_OF(sys->n), HB_MAXBLOCK_OF(sys->n)))) return rc;
-    CU(cudaMemcpyAsync(hout, cout, (size_t)n * out_d * out_batches * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (flags) CU(cudaMemcpyAsync(flags + i0, (int32_t*)dfl + i0, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+    if (chunks == 1) { ac.N = N; ac.in = (const double*)din; ac.out = (double*)dout; ac.flags = flags ? (int*)dfl : nullptr; }
+    else { ac.N = n; ac.in = cin; ac.out = cout; ac.flags = flags ? (int*)dfl + i0 : nullptr; }
+    if ((rc = launch(fn, ac, chunks == 1 ? N : n, s_k, HB_BLOCK_OF(sys->n), HB_MAXBLOCK_OF(sys->n), sys->dyn_doubles))) return rc;
+    CU(cudaEventRecord(done, s_k));
+    CU(cudaStreamWaitEvent(s_down, done, 0));
+    if (chunks == 1) {
+      CU(cudaMemcpyAsync(out, dout, out_bytes, cudaMemcpyDeviceToHost, s_down));
+      if (flags) CU(cudaMemcpyAsync(flags, dfl, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, s_down));
+    } else {
+      CU(cudaMemcpyAsync(hout, cout, (size_t)n * out_d * sizeof(double), cudaMemcpyDeviceToHost, s_down));
+      if (flags) CU(cudaMemcpyAsync(flags + i0, (int32_t*)dfl + i0, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s_down));
+    }
   }
-  for (int k = 0; k < 3 && k < chunks; k++) CU(cudaStreamSynchronize(g_scratch.streams[k]));
+  CU(cudaStreamSynchronize(s_down));   // the last download is the last operation of the call
   return HB_OK;
 }
 
@@ -372,6 +436,7 @@ hb_status hb_system_builtin(hb_builtin id, const double* params, int32_t n_param
   std::vector<double> dflt;
   hb::builtin_params(id, nullptr, 0, dflt);
   s->baked = std::getenv("HB_NO_BAKED") == nullptr && dflt == s->params;
+  s->dyn_doubles = hb_aot_dyn_doubles((int)id + (s->baked ? HB_SYS__COUNT : 0));
   if (s->baked) spec.baked_params = dflt;
   if (hb_aot_kargs_size() != sizeof(HbKArgs)) { delete s; return fail(HB_ERR_INVALID, "internal: host/device HbKArgs layout mismatch"); }
   hb::GeneratedSystem g;
@@ -406,6 +471,7 @@ hb_status hb_system_from_tape(int32_t m, int32_t n, const double* inertia, const
   s->params.assign(params, params + n_params);
   s->source = g.source;
   s->gen = g;
+  s->dyn_doubles = HB_DYN_DOUBLES(n, g.ne);
   s->arch = jit_arch();
   s->no_code = std::getenv("HB_JIT_SKIP_COMPILE") != nullptr;   // diagnostics: symbolic stage only, system cannot launch
   const char* lz = std::getenv("HB_JIT_LAZY");

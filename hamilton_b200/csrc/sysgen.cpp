@@ -522,6 +522,7 @@ bool generate_system(const SystemSpec& spec, const std::string& name, GeneratedS
   out.source = os.str();
   out.m = m; out.n = n; out.nj = NJ; out.nh = NH;
   out.n_nodes = (int)G.nodes.size();
+  out.ne = SH.ok ? (int)SH.carried.size() : 0;
   return true;
 }
 

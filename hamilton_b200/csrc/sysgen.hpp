@@ -30,6 +30,7 @@ struct GeneratedSystem {
   std::string source;    // the struct definition (no includes, no kernels)
   int m = 0, n = 0, nj = 0, nh = 0;
   int n_nodes = 0;       // size of the derivative DAG (diagnostics)
+  int ne = 0;            // values hpre hands to hpost (Sys::NE; 0 when the direct contraction is used)
 };
 
 // Differentiates the tapes symbolically and prints `struct <name> { ... }` for engine/hb_engine.cuh.

@@ -5,7 +5,7 @@ obj, kern = sys.argv[1], sys.argv[2]
 out = subprocess.check_output(["cuobjdump", "-sass", "-fun", kern, obj], text=True)
 ins = []
 for l in out.split('\n'):
-    m = re.match(r"\s+/\*([0-9a-f]{4})\*/\s+(.*?);", l)
+    m = re.match(r"\s+/\*([0-9a-f]{4,6})\*/\s+(.*?);", l)
     if m: ins.append((int(m.group(1), 16), m.group(2).strip()))
 best = None
 def has_lds(lo, hi): return any(lo <= a <= hi and t.startswith("LDS") for a, t in ins)
