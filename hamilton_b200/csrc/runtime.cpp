@@ -35,6 +35,7 @@ static const char* const KERNEL_KINDS[K_COUNT] = {"step_rk4", "step_rkf45", "evo
 #define HB_BLOCK 128
 #define HB_BLOCK_OF(NCOORD) 128   // must match engine/hb_engine.cuh
 #define HB_BIG_N 8
+#define HB_WSTORE_MAXD 8   // must match engine/hb_engine.cuh
 #define HB_DYN_DOUBLES(NCOORD, NE_) ((NCOORD) >= HB_BIG_N ? 3 * 2 * (NCOORD) + (NE_) : 0)
 #define HB_MAXBLOCK_OF(NCOORD) HB_BLOCK_OF(NCOORD)
 
@@ -183,8 +184,37 @@ struct hb_system {
 
 namespace {
 
+// Identity of one captured host-staging pipeline (run_batch): kernel, caller buffers, device scratch and every argument.
+struct HostPipeKey {
+  const void *fn, *in, *out, *flags, *din, *dout, *dfl;
+  int64_t N, chunks;
+  int in_d, out_d, dyn, pad_;
+  HbKArgs a;
+};
+
 // Device scratch for HB_MEM_HOST calls: per-thread, grow-only, with a private stream.
 struct Scratch {
+  // small most-recently-used cache of instantiated chunk-pipeline graphs
+  struct Pipe { HostPipeKey key; cudaGraphExec_t exec; };
+  std::vector<Pipe> pipes;
+  cudaGraphExec_t find_pipe(const HostPipeKey& k) {
+    for (size_t i = 0; i < pipes.size(); i++)
+      if (std::memcmp(&pipes[i].key, &k, sizeof k) == 0) {
+        Pipe hit = pipes[i];
+        pipes.erase(pipes.begin() + i);
+        pipes.insert(pipes.begin(), hit);
+        return hit.exec;
+      }
+    return nullptr;
+  }
+  void add_pipe(const HostPipeKey& k, cudaGraphExec_t e) {
+    if (pipes.size() >= 8) { cudaGraphExecDestroy(pipes.back().exec); pipes.pop_back(); }
+    pipes.insert(pipes.begin(), Pipe{k, e});
+  }
+  void drop_pipes() {
+    for (auto& p : pipes) cudaGraphExecDestroy(p.exec);
+    pipes.clear();
+  }
   void* p[3] = {nullptr, nullptr, nullptr};
   size_t cap[3] = {0, 0, 0};
   cudaStream_t stream = nullptr;      // == streams[0]
@@ -207,6 +237,7 @@ struct Scratch {
       for (auto& st : streams) if (st) { cudaStreamDestroy(st); st = nullptr; }
       for (auto e : events) cudaEventDestroy(e);
       events.clear();
+      drop_pipes();
       stream = nullptr;
       device = dev;
     }
@@ -313,11 +344,14 @@ hb_status run_batch(const hb_system* sys, int kid, HbKArgs a, int64_t N, hb_mems
     if (dts) cudaFreeAsync(dts, st);
     return rc;
   }
-  // HB_MEM_HOST, page-locked buffers, opt-in (HB_HOST_DIRECT=1): ONE kernel reads the Phases straight out of host memory
-  // and writes the results straight back (zero-copy).  Right for coherent CPU<->GPU links; over PCIe gen5 it measured 2x
-  // SLOWER than the staged pipeline below (4.5e8 vs 8.8e8 steps/s on config 2, profiles/r1f), so it is off by default.
-  static const bool direct_ok = [] { const char* e = std::getenv("HB_HOST_DIRECT"); return e && e[0] == '1'; }();
-  if (direct_ok) {
+  // HB_MEM_HOST, page-locked (mapped) caller buffers: ONE kernel reads the Phases straight out of host memory and writes
+  // the results straight back over PCIe — no staging copies, no fill/drain of a chunk pipeline, reads and writes overlap
+  // inside the kernel.  SM loads from host memory run at the link rate (50.9 GB/s measured, profiles/r1h/zc.txt); stores
+  // do only when every warp instruction writes whole sectors (53.6 vs 12.7 GB/s), hence the warp-transposed store
+  // (kernel layout 2, records of <= HB_WSTORE_MAXD doubles) or the SOA layout.  HB_HOST_DIRECT=0 forces staging.
+  static const bool direct_ok = [] { const char* e = std::getenv("HB_HOST_DIRECT"); return !(e && e[0] == '0'); }();
+  const bool direct_shape = a.layout == HB_LAYOUT_SOA || (out_d % 2 == 0 && out_d <= HB_WSTORE_MAXD);
+  if (direct_ok && direct_shape) {
     auto pinned_dev = [](const void* h, void** d) {
       cudaPointerAttributes at;
       if (cudaPointerGetAttributes(&at, h) != cudaSuccess) { cudaGetLastError(); return false; }
@@ -332,6 +366,7 @@ hb_status run_batch(const hb_system* sys, int kid, HbKArgs a, int64_t N, hb_mems
       cudaStream_t st = g_scratch.stream;
       if (ts) { CU(cudaMemcpyAsync(dts, ts, sizeof(double) * s, cudaMemcpyHostToDevice, st)); a.ts = (const double*)dts; }
       a.in = (const double*)din_h; a.out = (double*)dout_h; a.flags = (int*)dfl_h;
+      if (a.layout == HB_LAYOUT_AOS) a.layout = 2;   // warp-transposed stores (engine/hb_engine.cuh hb_store)
       if ((rc = launch(fn, a, N, st, HB_BLOCK_OF(sys->n), HB_MAXBLOCK_OF(sys->n), sys->dyn_doubles))) return rc;
       CU(cudaStreamSynchronize(st));
       return HB_OK;
@@ -347,51 +382,108 @@ hb_status run_batch(const hb_system* sys, int kid, HbKArgs a, int64_t N, hb_mems
   if (flags && (rc = g_scratch.get(2, sizeof(int32_t) * N, &dfl))) return rc;
   // Three decoupled in-order queues joined by events: every H2D copy sits back to back on the upload stream, the kernel
   // of chunk c waits only for its own upload, the D2H copy of chunk c only for its own kernel — both PCIe directions
-  // stay busy for the whole call except for one chunk of fill and one of drain.
+  // stay busy for the whole call except for one chunk of fill and one of drain: T ~ (1 + 1/chunks) x one-way copy time
+  // + chunks x per-chunk submission cost.
   static const int chunks_env = [] { const char* e = std::getenv("HB_HOST_CHUNKS"); int t = e ? std::atoi(e) : 0; return (t >= 1 && t <= 64) ? t : 0; }();
+  static const bool graph_ok = [] { const char* e = std::getenv("HB_HOST_GRAPH"); return !(e && e[0] == '0'); }();
+  // Page-locked caller buffers: the whole chunk pipeline is captured ONCE into a CUDA graph, cached per (kernel, buffers,
+  // arguments), and replayed with a single cudaGraphLaunch on later calls — a stepping loop over fixed buffers then pays
+  // one API call per step instead of 7 per chunk, which is what allows small chunks (short fill/drain).
+  auto pinned = [](const void* h) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, h) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+  };
+  const bool chunkable = a.layout == HB_LAYOUT_AOS && out_batches == 1 && !ts && N >= (1 << 16);
+  const bool use_graph = graph_ok && chunkable && pinned(in) && pinned(out) && (!flags || pinned(flags));
   int64_t chunks = 1;
-  if (a.layout == HB_LAYOUT_AOS && out_batches == 1 && !ts && N >= (1 << 16)) {
-    chunks = chunks_env ? chunks_env : N >> 14;     // >= 16 Ki trajectories per chunk
-    if (chunks > 32) chunks = chunks_env ? chunks_env : 32;
+  if (chunkable) {
+    // >= 2 MiB per chunk when replayed from a graph, >= 8 MiB when every chunk costs 7 stream API calls
+    const size_t per = use_graph ? ((size_t)2 << 20) : ((size_t)8 << 20);
+    chunks = chunks_env ? chunks_env : (int64_t)(in_bytes / per);
+    if (!chunks_env && chunks > (use_graph ? 16 : 4)) chunks = use_graph ? 16 : 4;
     if (chunks < 1) chunks = 1;
   }
   cudaStream_t s_up = g_scratch.streams[0], s_k = g_scratch.streams[1], s_down = g_scratch.streams[2];
-  if ((rc = g_scratch.need_events((int)(2 * chunks)))) return rc;
-  if (ts) {
-    double* dts = (double*)((char*)din + in_bytes);
-    CU(cudaMemcpyAsync(dts, ts, sizeof(double) * s, cudaMemcpyHostToDevice, s_up));
-    a.ts = dts;
-  }
-  for (int64_t c = 0; c < chunks; c++) {
-    const int64_t i0 = N * c / chunks, i1 = N * (c + 1) / chunks, n = i1 - i0;
-    const double* hin = in + (size_t)i0 * in_d;
-    double* hout = out + (size_t)i0 * out_d;
-    double* cin = (double*)din + (size_t)i0 * in_d;
-    double* cout = inplace ? cin : (double*)dout + (size_t)i0 * out_d;
-    cudaEvent_t up = g_scratch.events[2 * c], done = g_scratch.events[2 * c + 1];
-    if (chunks == 1) {   // whole batch (any layout, evolve output): copy everything
-      CU(cudaMemcpyAsync(din, in, in_bytes, cudaMemcpyHostToDevice, s_up));
-      if (flags) CU(cudaMemcpyAsync(dfl, flags, sizeof(int32_t) * N, cudaMemcpyHostToDevice, s_up));
-    } else {
-      CU(cudaMemcpyAsync(cin, hin, (size_t)n * in_d * sizeof(double), cudaMemcpyHostToDevice, s_up));
-      if (flags) CU(cudaMemcpyAsync((int32_t*)dfl + i0, flags + i0, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s_up));
+  if ((rc = g_scratch.need_events((int)(2 * chunks) + 1))) return rc;
+  const int blk = HB_BLOCK_OF(sys->n), max_blk = HB_MAXBLOCK_OF(sys->n);
+  if (resident_ctas(fn, blk, (size_t)sys->dyn_doubles * sizeof(double) * blk) < 0)   // (also keeps this query out of a capture)
+    return fail(HB_ERR_CUDA, "kernel needs more dynamic shared memory than the device offers");
+  auto enqueue = [&]() -> hb_status {
+    if (ts) {
+      double* dts = (double*)((char*)din + in_bytes);
+      CU(cudaMemcpyAsync(dts, ts, sizeof(double) * s, cudaMemcpyHostToDevice, s_up));
+      a.ts = dts;
     }
-    CU(cudaEventRecord(up, s_up));
-    CU(cudaStreamWaitEvent(s_k, up, 0));
-    HbKArgs ac = a;
-    if (chunks == 1) { ac.N = N; ac.in = (const double*)din; ac.out = (double*)dout; ac.flags = flags ? (int*)dfl : nullptr; }
-    else { ac.N = n; ac.in = cin; ac.out = cout; ac.flags = flags ? (int*)dfl + i0 : nullptr; }
-    if ((rc = launch(fn, ac, chunks == 1 ? N : n, s_k, HB_BLOCK_OF(sys->n), HB_MAXBLOCK_OF(sys->n), sys->dyn_doubles))) return rc;
-    CU(cudaEventRecord(done, s_k));
-    CU(cudaStreamWaitEvent(s_down, done, 0));
-    if (chunks == 1) {
-      CU(cudaMemcpyAsync(out, dout, out_bytes, cudaMemcpyDeviceToHost, s_down));
-      if (flags) CU(cudaMemcpyAsync(flags, dfl, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, s_down));
-    } else {
-      CU(cudaMemcpyAsync(hout, cout, (size_t)n * out_d * sizeof(double), cudaMemcpyDeviceToHost, s_down));
-      if (flags) CU(cudaMemcpyAsync(flags + i0, (int32_t*)dfl + i0, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s_down));
+    for (int64_t c = 0; c < chunks; c++) {
+      const int64_t i0 = N * c / chunks, i1 = N * (c + 1) / chunks, n = i1 - i0;
+      const double* hin = in + (size_t)i0 * in_d;
+      double* hout = out + (size_t)i0 * out_d;
+      double* cin = (double*)din + (size_t)i0 * in_d;
+      double* cout = inplace ? cin : (double*)dout + (size_t)i0 * out_d;
+      cudaEvent_t up = g_scratch.events[2 * c], done = g_scratch.events[2 * c + 1];
+      if (chunks == 1) {   // whole batch (any layout, evolve output): copy everything
+        CU(cudaMemcpyAsync(din, in, in_bytes, cudaMemcpyHostToDevice, s_up));
+        if (flags) CU(cudaMemcpyAsync(dfl, flags, sizeof(int32_t) * N, cudaMemcpyHostToDevice, s_up));
+      } else {
+        CU(cudaMemcpyAsync(cin, hin, (size_t)n * in_d * sizeof(double), cudaMemcpyHostToDevice, s_up));
+        if (flags) CU(cudaMemcpyAsync((int32_t*)dfl + i0, flags + i0, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s_up));
+      }
+      CU(cudaEventRecord(up, s_up));
+      CU(cudaStreamWaitEvent(s_k, up, 0));
+      HbKArgs ac = a;
+      if (chunks == 1) { ac.N = N; ac.in = (const double*)din; ac.out = (double*)dout; ac.flags = flags ? (int*)dfl : nullptr; }
+      else { ac.N = n; ac.in = cin; ac.out = cout; ac.flags = flags ? (int*)dfl + i0 : nullptr; }
+      hb_status lrc = launch(fn, ac, chunks == 1 ? N : n, s_k, blk, max_blk, sys->dyn_doubles);
+      if (lrc) return lrc;
+      CU(cudaEventRecord(done, s_k));
+      CU(cudaStreamWaitEvent(s_down, done, 0));
+      if (chunks == 1) {
+        CU(cudaMemcpyAsync(out, dout, out_bytes, cudaMemcpyDeviceToHost, s_down));
+        if (flags) CU(cudaMemcpyAsync(flags, dfl, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, s_down));
+      } else {
+        CU(cudaMemcpyAsync(hout, cout, (size_t)n * out_d * sizeof(double), cudaMemcpyDeviceToHost, s_down));
+        if (flags) CU(cudaMemcpyAsync(flags + i0, (int32_t*)dfl + i0, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s_down));
+      }
+    }
+    return HB_OK;
+  };
+  if (use_graph && chunks > 1) {
+    HostPipeKey key;
+    std::memset(&key, 0, sizeof key);
+    key.fn = fn; key.in = in; key.out = out; key.flags = flags; key.din = din; key.dout = dout; key.dfl = dfl;
+    key.N = N; key.chunks = chunks; key.in_d = in_d; key.out_d = out_d; key.dyn = sys->dyn_doubles; key.a = a;
+    cudaGraphExec_t exec = g_scratch.find_pipe(key);
+    if (!exec) {
+      cudaGraph_t graph = nullptr;
+      CU(cudaStreamBeginCapture(s_up, cudaStreamCaptureModeThreadLocal));
+      rc = enqueue();
+      cudaError_t e1 = cudaSuccess, e2 = cudaSuccess;
+      if (!rc) {   // join the kernel and download queues back into the origin stream
+        cudaEvent_t fin = g_scratch.events[2 * chunks];
+        e1 = cudaEventRecord(fin, s_down);
+        if (e1 == cudaSuccess) e1 = cudaStreamWaitEvent(s_up, fin, 0);
+      }
+      e2 = cudaStreamEndCapture(s_up, &graph);
+      if (rc || e1 != cudaSuccess || e2 != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        if (rc) return rc;
+        exec = nullptr;   // capture not possible here: fall through to plain stream submission
+      } else {
+        cudaError_t e3 = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e3 != cudaSuccess) { cudaGetLastError(); exec = nullptr; }
+        else g_scratch.add_pipe(key, exec);
+      }
+    }
+    if (exec) {
+      CU(cudaGraphLaunch(exec, s_up));
+      CU(cudaStreamSynchronize(s_up));
+      return HB_OK;
     }
   }
+  if ((rc = enqueue())) return rc;
   CU(cudaStreamSynchronize(s_down));   // the last download is the last operation of the call
   return HB_OK;
 }

@@ -253,6 +253,24 @@ def test_large_batch_properties_at_full_size():
     assert int(fl.sum()) == 0
 
 
+@pytest.mark.parametrize("env", [{}, {"HB_HOST_DIRECT": "0"}, {"HB_HOST_DIRECT": "0", "HB_HOST_GRAPH": "0"}],
+                         ids=["zero_copy", "staged_graph", "staged_streams"])
+def test_host_paths_match_device_path(env):
+    """The three HB_MEM_HOST data paths (picked per process by environment, so each runs in its own interpreter):
+    zero-copy kernel on page-locked buffers, chunked staging replayed from a cached CUDA graph, chunked staging
+    submitted to three streams.  tests/host_paths_check.py compares each bit for bit with the device-pointer path."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    e = dict(os.environ)
+    e.update(env)
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "host_paths_check.py")], cwd=root, env=e,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "host paths ok" in r.stdout
+
+
 def test_out_of_domain_angles_take_the_slow_path(oracle_mod):
     """|q| >= 1e5 leaves the fast sincos domain: those trajectories are redone out of line with libdevice math.
     Mixed in one warp with ordinary trajectories; also in-place (y_out == y_in) so the retry must re-read intact input."""
