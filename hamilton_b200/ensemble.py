@@ -12,9 +12,10 @@ def shard(n_total, rank, world):
     return first, n_total * (rank + 1) // world - first
 
 
-def gather_final(local, n_total=None, group=None):
+def gather_final(local, n_total=None, group=None, out=None):
     """All-gather of per-rank AOS batches [count_r, d] into the full [N, d] array on every rank
-    (NCCL over NVLink on GPU tensors, gloo on CPU tensors).  Handles uneven shards by padding."""
+    (NCCL over NVLink on GPU tensors, gloo on CPU tensors).  Handles uneven shards by padding.
+    `out` (optional, even shards only): preallocated [world * count, d] destination, so that a timed gather holds no allocation."""
     import torch
     import torch.distributed as dist
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
@@ -26,7 +27,9 @@ def gather_final(local, n_total=None, group=None):
     all_counts = [int(c.item()) for c in all_counts]
     cmax = max(all_counts)
     if all(c == cmax for c in all_counts):
-        out = torch.empty((world * cmax,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        shape = (world * cmax,) + tuple(local.shape[1:])
+        if out is None or tuple(out.shape) != shape or out.dtype != local.dtype or out.device != local.device:
+            out = torch.empty(shape, dtype=local.dtype, device=local.device)
         dist.all_gather_into_tensor(out, local.contiguous(), group=group)
         return out
     pad = torch.zeros((cmax,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)

@@ -1,0 +1,61 @@
+// Does a DFMA with three REGISTER operands still issue every 2 clocks per scheduler?  8 warps/SMSP, 8 chains per thread.
+//   A: x = fma(x, const, const)   B: x = fma(x, y_reg, const)   C: x = fma(x, y_reg, z_reg)   D: x = fma(y_reg, z_reg, x)
+//   F: x = fma(x, y_reg, y_reg) (3 reads, 2 distinct)   G: x = fma(x, x, z_reg)   H: x = fma(x, Y, Z), Y and Z the same two registers for all chains
+//   E: C with 24 FFMA-pipe integer instructions mixed in per 64 DFMA (issue-slot pressure like the RK4 kernel: 77 per 224)
+// build: nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o exp_fp64b exp_fp64b.cu
+#include <cstdio>
+#include <cuda_runtime.h>
+template <int MODE>
+__global__ void k(double* out, long long* cyc, const double* in, int iters, double a, double b) {
+  constexpr int CH = 8;
+  double x[CH], y[CH], z[CH];
+  unsigned m = threadIdx.x;
+#pragma unroll
+  for (int c = 0; c < CH; c++) { x[c] = in[threadIdx.x + 32 * c]; y[c] = in[threadIdx.x + 32 * c + 1024]; z[c] = in[threadIdx.x + 32 * c + 2048]; }
+  const long long t0 = clock64();
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+#pragma unroll
+      for (int c = 0; c < CH; c++) {
+        if (MODE == 0) x[c] = fma(x[c], a, b);
+        if (MODE == 1) x[c] = fma(x[c], y[c], b);
+        if (MODE == 2 || MODE == 4) x[c] = fma(x[c], y[c], z[(c + u) % CH]);
+        if (MODE == 3) x[c] = fma(y[c], z[(c + u) % CH], x[c]);
+        if (MODE == 5) x[c] = fma(x[c], y[c], y[c]);
+        if (MODE == 6) x[c] = fma(x[c], x[c], z[c]);
+        if (MODE == 7) x[c] = fma(x[c], y[0], z[0]);
+      }
+      if (MODE == 4) {
+#pragma unroll
+        for (int q = 0; q < 3; q++) m = (m * 1664525u + 1013904223u) ^ (m >> 7);
+      }
+    }
+  }
+  const long long t1 = clock64();
+  double s = (double)m;
+#pragma unroll
+  for (int c = 0; c < CH; c++) s += x[c];
+  if (s == 1.2345) out[0] = s;
+  if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+template <int MODE>
+void run(int sms, const double* in) {
+  const int block = 1024, grid = sms, iters = 2048;
+  double* out; long long* cyc; cudaMalloc(&out, 8); cudaMalloc(&cyc, 8 * grid);
+  k<MODE><<<grid, block>>>(out, cyc, in, 16, 1.0000001, 1e-9);
+  k<MODE><<<grid, block>>>(out, cyc, in, iters, 1.0000001, 1e-9);
+  cudaDeviceSynchronize();
+  long long* h = new long long[grid]; cudaMemcpy(h, cyc, 8 * grid, cudaMemcpyDeviceToHost);
+  double avg = 0; for (int i = 0; i < grid; i++) avg += h[i]; avg /= grid;
+  printf("mode %c: %.1f DFMA lanes/clk/SM\n", 'A' + MODE, (double)iters * 64 * block / avg);
+  cudaFree(out); cudaFree(cyc); delete[] h;
+}
+int main() {
+  int sms; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  double* in; cudaMalloc(&in, 8 * 4096);
+  double h[4096]; for (int i = 0; i < 4096; i++) h[i] = 1.0 + 1e-9 * (i % 97);
+  cudaMemcpy(in, h, sizeof h, cudaMemcpyHostToDevice);
+  run<0>(sms, in); run<1>(sms, in); run<2>(sms, in); run<3>(sms, in); run<4>(sms, in); run<5>(sms, in); run<6>(sms, in); run<7>(sms, in);
+  return 0;
+}
