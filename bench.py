@@ -318,6 +318,14 @@ def main():
                 prof = json.load(f)
             traffic = prof.get("dram_bytes_per_launch")
             fp64 = prof.get("fp64")
+            # live FP64 view: issue cycles the step needs on the FP64 pipe (static SASS count, 3-operand DFMAs at 3 clocks)
+            # against the cycles the schedulers had — the resource that actually binds this kernel
+            cyc = fp64.get("fp64_issue_cycles_per_rk4_step") if fp64 else None
+            mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz")
+            if cyc and mhz:
+                sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+                bound = sms * 4 * 32 * mhz * 1e6 / cyc                # steps/s per GPU at 100 % FP64 issue
+                fp64 = dict(fp64, fp64_bound_steps_per_s_at_measured_clock=bound, achieved_frac_of_fp64_bound=value / world / bound)
         except Exception:
             pass
         cpu_v = cpu_sample = cpu_threads = None

@@ -349,18 +349,19 @@ hb_status run_batch(const hb_system* sys, int kid, HbKArgs a, int64_t N, hb_mems
   // inside the kernel.  SM loads from host memory run at the link rate (50.9 GB/s measured, profiles/r1h/zc.txt); stores
   // do only when every warp instruction writes whole sectors (53.6 vs 12.7 GB/s), hence the warp-transposed store
   // (kernel layout 2, records of <= HB_WSTORE_MAXD doubles) or the SOA layout.  HB_HOST_DIRECT=0 forces staging.
-  static const bool direct_ok = [] { const char* e = std::getenv("HB_HOST_DIRECT"); return !(e && e[0] == '0'); }();
+  static const int direct_mode = [] { const char* e = std::getenv("HB_HOST_DIRECT"); return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1; }();
   const bool direct_shape = a.layout == HB_LAYOUT_SOA || (out_d % 2 == 0 && out_d <= HB_WSTORE_MAXD);
-  if (direct_ok && direct_shape) {
-    auto pinned_dev = [](const void* h, void** d) {
-      cudaPointerAttributes at;
-      if (cudaPointerGetAttributes(&at, h) != cudaSuccess) { cudaGetLastError(); return false; }
-      if (at.type != cudaMemoryTypeHost || !at.devicePointer) return false;
-      *d = at.devicePointer;
-      return true;
-    };
-    void *din_h = nullptr, *dout_h = nullptr, *dfl_h = nullptr;
-    if (pinned_dev(in, &din_h) && pinned_dev(out, &dout_h) && (!flags || pinned_dev(flags, &dfl_h))) {
+  auto pinned_dev = [](const void* h, void** d) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, h) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (at.type != cudaMemoryTypeHost || !at.devicePointer) return false;
+    *d = at.devicePointer;
+    return true;
+  };
+  void *din_h = nullptr, *dout_h = nullptr, *dfl_h = nullptr;
+  const bool mapped = direct_mode && direct_shape && pinned_dev(in, &din_h) && pinned_dev(out, &dout_h) && (!flags || pinned_dev(flags, &dfl_h));
+  if (mapped && direct_mode == 1) {
+    {
       void* dts = nullptr;
       if ((rc = g_scratch.get(0, ts ? sizeof(double) * s : 8, &dts))) return rc;
       cudaStream_t st = g_scratch.stream;
@@ -395,6 +396,9 @@ hb_status run_batch(const hb_system* sys, int kid, HbKArgs a, int64_t N, hb_mems
     return at.type == cudaMemoryTypeHost;
   };
   const bool chunkable = a.layout == HB_LAYOUT_AOS && out_batches == 1 && !ts && N >= (1 << 16);
+  // HB_HOST_DIRECT=2 (hybrid): the copy engine uploads the chunks, the kernel of each chunk stores straight into the
+  // caller's page-locked output (warp-transposed) — no download copies, no duplex copy-engine traffic.
+  const bool hybrid = mapped && direct_mode == 2 && chunkable;
   const bool use_graph = graph_ok && chunkable && pinned(in) && pinned(out) && (!flags || pinned(flags));
   int64_t chunks = 1;
   if (chunkable) {
@@ -427,15 +431,21 @@ hb_status run_batch(const hb_system* sys, int kid, HbKArgs a, int64_t N, hb_mems
         if (flags) CU(cudaMemcpyAsync(dfl, flags, sizeof(int32_t) * N, cudaMemcpyHostToDevice, s_up));
       } else {
         CU(cudaMemcpyAsync(cin, hin, (size_t)n * in_d * sizeof(double), cudaMemcpyHostToDevice, s_up));
-        if (flags) CU(cudaMemcpyAsync((int32_t*)dfl + i0, flags + i0, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s_up));
+        if (flags && !hybrid) CU(cudaMemcpyAsync((int32_t*)dfl + i0, flags + i0, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s_up));
       }
       CU(cudaEventRecord(up, s_up));
       CU(cudaStreamWaitEvent(s_k, up, 0));
       HbKArgs ac = a;
       if (chunks == 1) { ac.N = N; ac.in = (const double*)din; ac.out = (double*)dout; ac.flags = flags ? (int*)dfl : nullptr; }
       else { ac.N = n; ac.in = cin; ac.out = cout; ac.flags = flags ? (int*)dfl + i0 : nullptr; }
+      if (hybrid) {
+        ac.out = (double*)dout_h + (size_t)i0 * out_d;
+        ac.flags = flags ? (int*)dfl_h + i0 : nullptr;   // read-modify-write in host memory, only for flagged trajectories
+        ac.layout = 2;
+      }
       hb_status lrc = launch(fn, ac, chunks == 1 ? N : n, s_k, blk, max_blk, sys->dyn_doubles);
       if (lrc) return lrc;
+      if (hybrid) { if (c + 1 == chunks) { CU(cudaEventRecord(done, s_k)); CU(cudaStreamWaitEvent(s_down, done, 0)); } continue; }
       CU(cudaEventRecord(done, s_k));
       CU(cudaStreamWaitEvent(s_down, done, 0));
       if (chunks == 1) {
@@ -452,7 +462,7 @@ hb_status run_batch(const hb_system* sys, int kid, HbKArgs a, int64_t N, hb_mems
     HostPipeKey key;
     std::memset(&key, 0, sizeof key);
     key.fn = fn; key.in = in; key.out = out; key.flags = flags; key.din = din; key.dout = dout; key.dfl = dfl;
-    key.N = N; key.chunks = chunks; key.in_d = in_d; key.out_d = out_d; key.dyn = sys->dyn_doubles; key.a = a;
+    key.N = N; key.chunks = chunks; key.in_d = in_d; key.out_d = out_d; key.dyn = sys->dyn_doubles; key.pad_ = hybrid ? 1 : 0; key.a = a;
     cudaGraphExec_t exec = g_scratch.find_pipe(key);
     if (!exec) {
       cudaGraph_t graph = nullptr;

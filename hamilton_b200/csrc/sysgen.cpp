@@ -456,11 +456,6 @@ bool generate_system(const SystemSpec& spec, const std::string& name, GeneratedS
   bool trig = false;
   for (const Node& nd : G.nodes) trig = trig || nd.op == Op::Sin || nd.op == Op::Cos;
   os << "  static constexpr bool TRIG = " << (trig ? "true" : "false") << ";\n";
-  // Register budget of the RK4 step kernel.  For a very cheap RHS, asking ptxas for 6 resident CTAs of 128 threads (80
-  // registers) is ABOVE what it would pick, and it spends the slack on instruction-level parallelism (two-body +5 %,
-  // pendulum +2 % at one step per launch); a cap below its own choice costs (double pendulum -3 %): profiles/r1m/ab_sr.txt.
-  const double rhs_cost = SH.ok ? SH.cost_sym : SH.cost_direct;
-  os << "  static constexpr int MINB_RK4 = " << ((n <= 2 && rhs_cost <= 40) ? 6 : 1) << ";   // min resident CTAs asked of ptxas for step_rk4\n";
   os << table_fn("jidx", "int i, int j", "i * N + j", jidx);
   os << table_fn("jrow", "int e", "e", jrow) << table_fn("jcol", "int e", "e", jcol);
   os << table_fn("hrow", "int e", "e", hrow) << table_fn("hj", "int e", "e", hj) << table_fn("hk", "int e", "e", hk);

@@ -23,5 +23,5 @@ for rep in range(3):
         s.batch_step(h_in[i % 2], 0.01, 1, integ=L.RK4, out=h_out[i % 2])
     torch.cuda.synchronize()
     best = min(best, (time.perf_counter() - t0) / steps)
-print("N=%d chunks=%s graph=%s: %.3f ms/call, %.4g steps/s, %.1f GB/s each way" % (
-    N, os.environ.get("HB_HOST_CHUNKS", "auto"), os.environ.get("HB_HOST_GRAPH", "1"), best * 1e3, N / best, N * 32 / best / 1e9))
+print("N=%d direct=%s chunks=%s graph=%s: %.3f ms/call, %.4g steps/s, %.1f GB/s each way" % (
+    N, os.environ.get("HB_HOST_DIRECT", "1"), os.environ.get("HB_HOST_CHUNKS", "auto"), os.environ.get("HB_HOST_GRAPH", "1"), best * 1e3, N / best, N * 32 / best / 1e9))

@@ -253,12 +253,12 @@ def test_large_batch_properties_at_full_size():
     assert int(fl.sum()) == 0
 
 
-@pytest.mark.parametrize("env", [{}, {"HB_HOST_DIRECT": "0"}, {"HB_HOST_DIRECT": "0", "HB_HOST_GRAPH": "0"}],
-                         ids=["zero_copy", "staged_graph", "staged_streams"])
+@pytest.mark.parametrize("env", [{}, {"HB_HOST_DIRECT": "2"}, {"HB_HOST_DIRECT": "0"}, {"HB_HOST_DIRECT": "0", "HB_HOST_GRAPH": "0"}],
+                         ids=["zero_copy", "hybrid", "staged_graph", "staged_streams"])
 def test_host_paths_match_device_path(env):
-    """The three HB_MEM_HOST data paths (picked per process by environment, so each runs in its own interpreter):
-    zero-copy kernel on page-locked buffers, chunked staging replayed from a cached CUDA graph, chunked staging
-    submitted to three streams.  tests/host_paths_check.py compares each bit for bit with the device-pointer path."""
+    """The HB_MEM_HOST data paths (picked per process by environment, so each runs in its own interpreter): zero-copy
+    kernel on page-locked buffers, copy-engine upload + kernels storing straight to the host, chunked staging replayed
+    from a cached CUDA graph, chunked staging submitted to three streams.  tests/host_paths_check.py compares each bit for bit with the device-pointer path."""
     import os
     import subprocess
     import sys
