@@ -135,6 +135,22 @@ class ClockSampler:
                 "sampled": ("NVML every ~1 ms, " if self.h is not None else "nvidia-smi -lms 20, ") + where}
 
 
+def bind_near_gpu(index):
+    """Pins this process to the CPUs NVML reports as local to GPU `index` (one rank per GPU: without it the ranks' host
+    buffers pile up on one socket and the e2e leg measures the inter-socket link).  Returns a short description."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(index).uuid)
+        h = pynvml.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        cpus = sorted(os.sched_getaffinity(0))
+        return "%d cpus near gpu %d (%d..%d)" % (len(cpus), index, cpus[0], cpus[-1])
+    except Exception as ex:
+        return "unbound (%s)" % type(ex).__name__
+
+
 def cpu_oracle_steps_per_sec(target_seconds, threads):
     """Times the oracle's RK4 on a bounded sample of the same workload (same RNG stream, first trajectories)."""
     from oracle import oracle as O
@@ -203,6 +219,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback in the product path)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    all_cpus = os.sched_getaffinity(0)
+    numa = bind_near_gpu(local_rank)       # page-locked host buffers of the e2e leg land on the GPU's own NUMA node
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -331,6 +349,7 @@ def main():
         cpu_v = cpu_sample = cpu_threads = None
         if world == 1:                                            # rank 0 at N=1 only
             from oracle import oracle as O
+            os.sched_setaffinity(0, all_cpus)                     # the CPU baseline uses every host core again
             cpu_threads = O.max_threads()
             cpu_v, cpu_sample = cpu_oracle_steps_per_sec(args.cpu_seconds, cpu_threads)
         out = {
@@ -345,7 +364,8 @@ def main():
             "clocks": clocks,
             "gpu_launches": args.steps,
             "e2e": {"value": world * N * e2e_steps / (e2e_ms * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": N * 32, "d2h_bytes_per_step": N * 32,
-                    "steps": e2e_steps, "call": "hb_batch_step(HB_INTEG_RK4, nsteps=1, HB_MEM_HOST) on pinned host arrays, blocking"},
+                    "steps": e2e_steps, "call": "hb_batch_step(HB_INTEG_RK4, nsteps=1, HB_MEM_HOST) on pinned host arrays, blocking",
+                    "host_binding": numa},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "kernel": "hbk_double_pendulum_dflt_step_rk4",
                          "algorithmic_bytes_per_launch": N * ALGO_BYTES_PER_STEP,

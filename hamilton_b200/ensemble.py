@@ -21,10 +21,15 @@ def gather_final(local, n_total=None, group=None, out=None):
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return local
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    counts = torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device)
-    all_counts = [torch.zeros_like(counts) for _ in range(world)]
-    dist.all_gather(all_counts, counts, group=group)
-    all_counts = [int(c.item()) for c in all_counts]
+    if n_total is not None:      # block split known to every rank: no count exchange, no host synchronisation
+        all_counts = [shard(n_total, r, world)[1] for r in range(world)]
+        if all_counts[rank] != local.shape[0]:
+            raise ValueError("local batch does not match shard(n_total, rank, world)")
+    else:
+        counts = torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device)
+        all_counts = [torch.zeros_like(counts) for _ in range(world)]
+        dist.all_gather(all_counts, counts, group=group)
+        all_counts = [int(c.item()) for c in all_counts]
     cmax = max(all_counts)
     if all(c == cmax for c in all_counts):
         shape = (world * cmax,) + tuple(local.shape[1:])
@@ -48,4 +53,4 @@ def run_ensemble(system, seed, n_total, lo, hi, dt, nsteps, integ=0, gather=True
     first, count = shard(n_total, rank, world)
     y = system.batch_init_random(seed, first, count, lo, hi)
     out = system.batch_step(y, dt, nsteps, integ=integ)
-    return gather_final(out) if gather else out
+    return gather_final(out, n_total=n_total) if gather else out

@@ -34,7 +34,9 @@ def sync():
 
 for _ in range(3):
     s.batch_step(a, 0.01, 1, integ=L.RK4, out=b)
-full = ensemble.gather_final(b)          # warms the communicator
+full = ensemble.gather_final(b, n_total=N_TOTAL)
+for _ in range(3):                       # warm the communicator at this message size
+    full = ensemble.gather_final(b, n_total=N_TOTAL, out=full)
 sync()
 e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
 e0.record()
@@ -44,7 +46,7 @@ for k in range(steps):                   # step k+1 consumes step k's output (pi
     s.batch_step(src, 0.01, 1, integ=L.RK4, out=dst)
     src, dst = dst, (scratch if dst is b else b)
 e1.record()
-full = ensemble.gather_final(src, out=full)
+full = ensemble.gather_final(src, n_total=N_TOTAL, out=full)
 e2.record()
 sync()
 t = torch.tensor([e0.elapsed_time(e1), e1.elapsed_time(e2)], dtype=torch.float64, device=dev)

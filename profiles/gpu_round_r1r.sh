@@ -1,8 +1,8 @@
 #!/bin/bash
-# consolidated round-1 pass of the final build: parity suite, smoke, both bench arms, the other configs, ncu launch list +
+# consolidated round-1 pass of the final build (r1r; r1o was the same pass on a 120-register build): parity suite, smoke, both bench arms, the other configs, ncu launch list +
 # full captures (double pendulum, triple pendulum, chain12), FP64/PCIe microbenchmarks
-mkdir -p gpurun_out/r1o
-O=gpurun_out/r1o
+mkdir -p gpurun_out/r1r
+O=gpurun_out/r1r
 ( time python -m pytest tests -m gpu -x -q ) > $O/pytest_gpu.log 2>&1; tail -4 $O/pytest_gpu.log
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1 | tee $O/smoke.txt
 python bench.py > $O/bench_n1.json 2> $O/bench_n1.err; tail -c 3800 $O/bench_n1.json; tail -3 $O/bench_n1.err
