@@ -253,6 +253,36 @@ def test_large_batch_properties_at_full_size():
     assert int(fl.sum()) == 0
 
 
+@pytest.mark.parametrize("name,log2n", [("pendulum", 21), ("two_body", 21), ("spring1d", 21), ("triple_pendulum", 20), ("chain12", 18)])
+def test_other_baseline_configs_at_full_size(name, log2n):
+    """BASELINE configs[2..4] at their full per-GPU sizes (2 x 2,097,152 mixed (2,1)/(4,2); 1,048,576 triple pendulums per
+    GPU; 262,144 twelve-link chains): energy drift of RK4, time reversal, AOS/SOA agreement, no failure flags, and
+    bit-identity with the same trajectories stepped as a small batch (results must not depend on the batch size,
+    grid shape or on which resident CTA a trajectory lands in)."""
+    import torch
+    sid, lo, hi = BOXES[name]
+    s = hb.systems.builtin(sid)
+    N = 1 << log2n
+    steps, dt = (20, 0.001) if name == "chain12" else (50, 0.001)
+    y0 = s.batch_init_random(SEED + 11, 0, N, lo, hi)
+    fl = torch.zeros(N, dtype=torch.int32, device=y0.device)
+    e0 = s.batch_energies(y0)[:, 2]
+    y1 = s.batch_step(y0, dt, steps, integ=L.RK4, flags=fl)
+    assert int(fl.sum()) == 0
+    e1 = s.batch_energies(y1)[:, 2]
+    scale = 1.0 + e0.abs()
+    assert float(((e1 - e0).abs() / scale).max()) < (1e-6 if name == "chain12" else 1e-7)
+    n = s.n
+    back = y1.clone(); back[:, n:] *= -1
+    y2 = s.batch_step(back, dt, steps, integ=L.RK4); y2[:, n:] *= -1
+    assert float((y2 - y0).abs().max()) < 1e-6
+    soa = s.batch_step(y0.t().contiguous(), dt, steps, integ=L.RK4, layout=L.SOA)
+    assert torch.equal(soa.t().contiguous(), y1)
+    idx = torch.tensor([0, 1, 31, 32, 12345, N // 2 + 7, N - 129, N - 1], device=y0.device)
+    small = s.batch_step(y0[idx].contiguous(), dt, steps, integ=L.RK4)
+    assert torch.equal(small, y1[idx])
+
+
 @pytest.mark.parametrize("env", [{}, {"HB_HOST_DIRECT": "2"}, {"HB_HOST_DIRECT": "0"}, {"HB_HOST_DIRECT": "0", "HB_HOST_GRAPH": "0"}],
                          ids=["zero_copy", "hybrid", "staged_graph", "staged_streams"])
 def test_host_paths_match_device_path(env):
