@@ -210,6 +210,15 @@ def _gloo_worker(rank, world, port, n_total, q):
     y = o.init_random(0x48414D49, first, count, lo, hi)            # what batch_init_random generates on each GPU
     out, _ = o.batch_step(y, 0, 0.01, 2)                             # stand-in for the GPU step (tests may use the oracle)
     full = hbm.ensemble.gather_final(torch.from_numpy(out))
+    # the same gather with the block split known up front (no count exchange) and, for even shards, a preallocated output
+    full2 = hbm.ensemble.gather_final(torch.from_numpy(out), n_total=n_total, out=torch.empty_like(full))
+    assert torch.equal(full, full2)
+    try:
+        hbm.ensemble.gather_final(torch.from_numpy(out), n_total=n_total + world)   # shard sizes no longer match
+        bad = False
+    except ValueError:
+        bad = True
+    assert bad
     q.put((rank, full.numpy()))
     dist.destroy_process_group()
 
