@@ -25,7 +25,7 @@
 #define HB_MAXP 64
 struct HbKArgs {
   const double* in; double* out; int* flags; const double* ts;
-  long long N; double dt; double dt6; int nsteps; int layout; int s; int substeps;
+  long long N; double dt; double dt6; double dth; int nsteps; int layout; int s; int substeps;
   unsigned long long seed; long long first;
   double prm[HB_MAXP];
 };
@@ -626,7 +626,7 @@ hb_status hb_batch_step(const hb_system* sys, hb_integrator integ, double dt, in
   if (integ != HB_INTEG_RK4 && integ != HB_INTEG_RKF45_GSL) return fail(HB_ERR_INVALID, "unknown integrator");
   if (nsteps < 0) return fail(HB_ERR_INVALID, "negative nsteps");
   if (integ == HB_INTEG_RKF45_GSL && !(dt > 0.0)) return fail(HB_ERR_INVALID, "RKF45_GSL needs dt > 0");
-  HbKArgs a; fill_params(sys, a); a.layout = layout; a.dt = dt; a.dt6 = dt / 6.0; a.nsteps = nsteps;
+  HbKArgs a; fill_params(sys, a); a.layout = layout; a.dt = dt; a.dt6 = dt / 6.0; a.dth = 0.5 * dt; a.nsteps = nsteps;
   return run_batch(sys, integ == HB_INTEG_RK4 ? K_STEP_RK4 : K_STEP_RKF45, a, N, mem, y_in, 2 * sys->n, y_out, 2 * sys->n, 1, flags,
                    nullptr, 0, stream);
 }
