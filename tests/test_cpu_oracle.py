@@ -140,6 +140,42 @@ def test_evolve_grid_semantics(oracle_mod):
     assert 0 < maxerr(out[-1], np.r_[q, p]) < 1e-6
 
 
+@pytest.mark.parametrize("sid,dt,nsteps", [(1, 0.01, 5), (1, 1.0 / 12, 12), (2, 1.0 / 12, 60), (3, 1.0 / 12, 12), (4, 0.05, 10)])
+def test_rkf45_two_restatements_agree(sid, dt, nsteps, oracle_mod):
+    """The C oracle's GSL-RKF45 (stepper + standard controller + evolve loop) against tests/ref_rkf45.py, a second
+    restatement written independently in Python, on the oracle's own hamEqs: same accepted/rejected step sequence, same
+    RHS count, states equal to rounding — iterated stepHam (fresh solve per step) and one evolveHam grid (h carried)."""
+    from tests import ref_rkf45 as R
+    o = oracle_mod.OracleSystem.builtin(sid)
+    n = o.n
+    name = [k for k, v in BOXES.items() if v[0] == sid][0]
+    y = random_phases(name, 3)[2]
+    if sid == 2:
+        y = np.array([-1.0, 0.25, np.cos(np.pi / 4), np.sin(np.pi / 4)])       # the room: walls force rejections
+
+    def f(v):
+        dq, dp = o.ham_eqs(v[:n], v[n:])
+        return np.r_[dq, dp]
+
+    q, p = y[:n].copy(), y[n:].copy()
+    yy = y.copy()
+    rejects = 0
+    for _ in range(nsteps):
+        q, p, st = o.step_ham(dt, q, p, stats=True)
+        rows, st2 = R.ode_solve(f, yy, [0.0, dt])
+        yy = rows[-1]
+        assert (st.steps, st.rejects, st.rhs_evals) == (st2.steps, st2.rejects, st2.rhs_evals)
+        assert maxerr(np.r_[q, p], yy) < 1e-12
+        rejects += st.rejects
+    if sid == 2:
+        assert rejects > 0
+    ts = np.linspace(0.0, 6 * dt, 7)
+    out, st = o.evolve_ham(y[:n], y[n:], ts, stats=True)
+    rows, st2 = R.ode_solve(f, y, ts)
+    assert (st.steps, st.rejects, st.rhs_evals) == (st2.steps, st2.rejects, st2.rhs_evals)
+    assert maxerr(out, rows) < 1e-11
+
+
 @pytest.mark.parametrize("name", NAMES)
 def test_golden_vectors_regression(name, oracle_mod, gold):
     g = gold[name]; n = g["n"]
