@@ -16,8 +16,9 @@
  *   Batches hold N independent trajectories in one of two layouts:
  *     HB_LAYOUT_AOS  y[i*2n + c]   (array of Phases; what a Storable vector of Phase looks like)
  *     HB_LAYOUT_SOA  y[c*N  + i]   (component-major; one coalesced stream per component)
- *   Buffers live either in host memory (HB_MEM_HOST: the library stages H2D/D2H itself) or in
- *   device memory of the current CUDA device (HB_MEM_DEVICE: zero-copy, asynchronous on `stream`).
+ *   Buffers live either in host memory (HB_MEM_HOST, blocking: page-locked mapped buffers are read and
+ *   written in place by the kernel over PCIe, anything else is staged H2D/D2H by the library) or in
+ *   device memory of the current CUDA device (HB_MEM_DEVICE: asynchronous on `stream`).
  *   Every function returns hb_status (0 = HB_OK); hb_last_error() gives a thread-local message.
  *   Numerical failures never abort: they set per-trajectory bits in the optional `flags` array
  *   (HB_FLAG_*), the analogue of hmatrix's `inv` exception / GSL error in the reference.
