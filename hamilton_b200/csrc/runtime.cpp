@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <nvrtc.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <cmath>
 #include <cstdio>
@@ -79,6 +81,7 @@ struct Nvrtc {
   decltype(&nvrtcGetProgramLog) GetProgramLog = nullptr;
   decltype(&nvrtcDestroyProgram) DestroyProgram = nullptr;
   decltype(&nvrtcGetErrorString) GetErrorString = nullptr;
+  decltype(&nvrtcVersion) Version = nullptr;
   std::string err;
   bool load() {
     if (h) return true;
@@ -87,7 +90,7 @@ struct Nvrtc {
     if (!h) { err = "cannot dlopen libnvrtc (needed to compile tape systems)"; return false; }
 #define SYM(x) x = (decltype(x))dlsym(h, "nvrtc" #x); if (!x) { err = "libnvrtc lacks nvrtc" #x; return false; }
     SYM(CreateProgram) SYM(CompileProgram) SYM(GetCUBINSize) SYM(GetCUBIN) SYM(GetProgramLogSize) SYM(GetProgramLog)
-    SYM(DestroyProgram) SYM(GetErrorString)
+    SYM(DestroyProgram) SYM(GetErrorString) SYM(Version)
 #undef SYM
     return true;
   }
@@ -109,7 +112,88 @@ std::string jit_arch() {
   return "sm_100a";   // the target this library is written for
 }
 
+// ---- on-disk cache of NVRTC output ------------------------------------------------------------
+// mkSystem is a compiler here (1-2 s for the reference's examples, over a minute for a 12-coordinate chain), and a host
+// program builds the same Systems on every start.  The cubin is therefore kept under $HB_JIT_CACHE_DIR (default
+// $XDG_CACHE_HOME/hamilton_b200 or ~/.cache/hamilton_b200), keyed by a 128-bit hash of everything that determines it:
+// the engine header, the generated translation unit, the architecture, the options and the NVRTC version.
+// HB_JIT_CACHE=0 disables it.  Files are written to a temporary name and renamed, so concurrent processes are safe.
+struct Hash128 {
+  unsigned long long a = 0xcbf29ce484222325ULL, b = 0x84222325cbf29ce4ULL;
+  void add(const void* p, size_t n) {
+    const unsigned char* c = (const unsigned char*)p;
+    for (size_t i = 0; i < n; i++) {
+      a = (a ^ c[i]) * 0x100000001b3ULL;                       // FNV-1a
+      b = (b + c[i] + 0x9e3779b97f4a7c15ULL) * 0xff51afd7ed558ccdULL; b ^= b >> 32;   // an unrelated second mix
+    }
+    const unsigned long long len = n;
+    for (int i = 0; i < 8; i++) { a = (a ^ ((len >> (8 * i)) & 0xff)) * 0x100000001b3ULL; }
+  }
+  void add(const std::string& s) { add(s.data(), s.size()); }
+  std::string hex() const { char buf[40]; std::snprintf(buf, sizeof buf, "%016llx%016llx", a, b); return buf; }
+};
+
+std::string jit_cache_dir() {
+  const char* off = std::getenv("HB_JIT_CACHE");
+  if (off && off[0] == '0') return "";
+  std::string d;
+  if (const char* e = std::getenv("HB_JIT_CACHE_DIR")) d = e;
+  else if (const char* x = std::getenv("XDG_CACHE_HOME")) d = std::string(x) + "/hamilton_b200";
+  else if (const char* h = std::getenv("HOME")) d = std::string(h) + "/.cache/hamilton_b200";
+  if (d.empty()) return "";
+  for (size_t i = 1; i <= d.size(); i++)                       // mkdir -p
+    if (i == d.size() || d[i] == '/') { std::string sub = d.substr(0, i); mkdir(sub.c_str(), 0777); }
+  struct stat st;
+  if (stat(d.c_str(), &st) != 0 || !S_ISDIR(st.st_mode) || access(d.c_str(), W_OK) != 0) return "";
+  return d;
+}
+
+bool read_file(const std::string& path, std::vector<char>& out) {
+  FILE* f = std::fopen(path.c_str(), "rb");
+  if (!f) return false;
+  std::fseek(f, 0, SEEK_END);
+  const long n = std::ftell(f);
+  std::fseek(f, 0, SEEK_SET);
+  bool ok = n > 4;
+  if (ok) { out.resize((size_t)n); ok = std::fread(out.data(), 1, (size_t)n, f) == (size_t)n; }
+  std::fclose(f);
+  return ok && out[0] == 0x7f && out[1] == 'E' && out[2] == 'L' && out[3] == 'F';   // a cubin is an ELF image
+}
+
+void write_file_atomic(const std::string& path, const std::vector<char>& data) {
+  char suffix[64];
+  std::snprintf(suffix, sizeof suffix, ".tmp.%ld.%p", (long)getpid(), (const void*)&data);
+  const std::string tmp = path + suffix;
+  FILE* f = std::fopen(tmp.c_str(), "wb");
+  if (!f) return;
+  const bool ok = std::fwrite(data.data(), 1, data.size(), f) == data.size();
+  if (std::fclose(f) != 0 || !ok || std::rename(tmp.c_str(), path.c_str()) != 0) std::remove(tmp.c_str());
+}
+
+bool nvrtc_compile_uncached(const std::string& src, const std::string& arch, std::vector<char>& cubin, std::string& log);
+
 bool nvrtc_compile(const std::string& src, const std::string& arch, std::vector<char>& cubin, std::string& log) {
+  const std::string dir = jit_cache_dir();
+  std::string path;
+  if (!dir.empty()) {
+    Hash128 h;
+    h.add(hb_engine_src, std::strlen(hb_engine_src));
+    h.add(src);
+    h.add(arch);
+    if (const char* e = std::getenv("HB_JIT_DEFINES")) h.add(e, std::strlen(e));
+    int vmaj = 0, vmin = 0;
+    { std::lock_guard<std::mutex> lk(g_nvrtc_mu); if (g_nvrtc.load() && g_nvrtc.Version) g_nvrtc.Version(&vmaj, &vmin); }
+    h.add(&vmaj, sizeof vmaj); h.add(&vmin, sizeof vmin);
+    path = dir + "/" + h.hex() + ".cubin";
+    if (read_file(path, cubin)) return true;
+    cubin.clear();
+  }
+  if (!nvrtc_compile_uncached(src, arch, cubin, log)) return false;
+  if (!path.empty()) write_file_atomic(path, cubin);
+  return true;
+}
+
+bool nvrtc_compile_uncached(const std::string& src, const std::string& arch, std::vector<char>& cubin, std::string& log) {
   std::lock_guard<std::mutex> lk(g_nvrtc_mu);
   if (!g_nvrtc.load()) { log = g_nvrtc.err; return false; }
   nvrtcProgram prog;

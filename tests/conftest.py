@@ -8,6 +8,10 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+# NVRTC output of tape systems is cached on disk (csrc/runtime.cpp); keep the cache inside the repository for test runs
+os.environ.setdefault("HB_JIT_CACHE_DIR", os.path.join(ROOT, ".jit_cache"))
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 

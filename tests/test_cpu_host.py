@@ -134,6 +134,48 @@ def test_nvrtc_compiles_a_tape_system_without_a_gpu():
     assert "hb_sincos" in s.source() and "struct HbSysJit" in s.source()
 
 
+def test_jit_disk_cache_hit_and_miss(tmp_path):
+    """The cubin of a tape system is kept on disk keyed by (engine header, generated source, arch, options, NVRTC version):
+    the second construction of the same System reads it back instead of compiling; a different System misses;
+    HB_JIT_CACHE=0 bypasses the cache; a corrupt file is ignored and replaced."""
+    import time
+    old = {k: os.environ.get(k) for k in ("HB_JIT_CACHE_DIR", "HB_JIT_CACHE")}
+    os.environ["HB_JIT_CACHE_DIR"] = str(tmp_path / "cache")
+    os.environ.pop("HB_JIT_CACHE", None)
+
+    def build(k):
+        t0 = time.perf_counter()
+        s = hb.mkSystem_([1.0, 1.0], lambda q: [num.sin(k * q[0]), 0.5 - num.cos(q[0])], lambda x: x[1], n=1)
+        return s, time.perf_counter() - t0
+
+    try:
+        _, t_cold = build(1.25)
+        files = sorted(os.listdir(tmp_path / "cache"))
+        assert len(files) == 1 and files[0].endswith(".cubin") and not any(".tmp." in f for f in files)
+        with open(tmp_path / "cache" / files[0], "rb") as f:
+            blob = f.read()
+        assert blob[:4] == b"\x7fELF"
+        _, t_warm = build(1.25)
+        assert sorted(os.listdir(tmp_path / "cache")) == files and t_warm < 0.5 * t_cold
+        build(1.75)                                                  # another System: another entry
+        assert len(os.listdir(tmp_path / "cache")) == 2
+        os.environ["HB_JIT_CACHE"] = "0"
+        _, t_off = build(1.25)
+        assert t_off > 2 * t_warm and len(os.listdir(tmp_path / "cache")) == 2
+        del os.environ["HB_JIT_CACHE"]
+        with open(tmp_path / "cache" / files[0], "wb") as f:         # a truncated / foreign file must not be loaded
+            f.write(b"garbage")
+        build(1.25)
+        with open(tmp_path / "cache" / files[0], "rb") as f:
+            assert f.read() == blob                                   # recompiled (deterministically) and rewritten
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
 def test_tape_validation_errors():
     lib = L.lib()
 
