@@ -255,7 +255,15 @@ struct hb_system {
         std::string log;
         if (!nvrtc_compile(hb::jit_translation_unit(gen, "hbk", KERNEL_KINDS[kid]), arch, cubins[slot], log)) return fail(HB_ERR_COMPILE, log);
       }
-      if (!libs[slot]) CU(cudaLibraryLoadData(&libs[slot], cubins[slot].data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+      if (!libs[slot] && cudaLibraryLoadData(&libs[slot], cubins[slot].data(), nullptr, nullptr, 0, nullptr, nullptr, 0) != cudaSuccess) {
+        // the image may have come from the disk cache (another driver, a damaged file): compile afresh once and retry
+        cudaGetLastError();
+        libs[slot] = nullptr;
+        std::string log;
+        const std::string tu = lazy ? hb::jit_translation_unit(gen, "hbk", KERNEL_KINDS[kid]) : hb::jit_translation_unit(gen, "hbk");
+        if (!nvrtc_compile_uncached(tu, arch, cubins[slot], log)) return fail(HB_ERR_COMPILE, log);
+        CU(cudaLibraryLoadData(&libs[slot], cubins[slot].data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+      }
       cudaKernel_t kh;
       std::string nm = std::string("hbk_") + KERNEL_KINDS[kid];
       CU(cudaLibraryGetKernel(&kh, libs[slot], nm.c_str()));
