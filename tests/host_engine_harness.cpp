@@ -1,0 +1,144 @@
+// Compiles the DEVICE engine (hamilton_b200/csrc/engine/hb_engine.cuh, with HB_HOST_EMU) together with a generated `Sys`
+// struct as HOST code: one emulated thread, CUDA built-ins stubbed.  Lets the CPU test-suite run the very code the
+// kernels inline — hamEqs (both generated forms), the closed-form / LDL^T solves, classical RK4 (register and
+// shared-memory variants), the GSL-RKF45 stepper + controller + evolve loop including its shortcut, the table-driven
+// sincos and the Newton reciprocal — against the oracle.  Test infrastructure: the product never computes on the CPU.
+#include <cmath>
+#include <cstring>
+#define HB_HOST_EMU 1
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __noinline__
+#define __constant__
+#define __restrict__
+#define __shared__ static
+#define __align__(n)
+struct double2 { double x, y; };
+static inline double2 make_double2(double x, double y) { double2 v; v.x = x; v.y = y; return v; }
+struct HbEmuDim { unsigned x, y, z; };
+static HbEmuDim threadIdx = {0, 0, 0}, blockIdx = {0, 0, 0}, blockDim = {128, 1, 1}, gridDim = {1, 1, 1};
+static inline int __double2hiint(double v) { long long b; std::memcpy(&b, &v, 8); return (int)(b >> 32); }
+static inline int __double2loint(double v) { long long b; std::memcpy(&b, &v, 8); return (int)(b & 0xffffffffLL); }
+static inline unsigned __activemask() { return 1u; }
+static inline void __syncwarp() {}
+static inline void __syncthreads() {}
+static inline unsigned long long __cvta_generic_to_shared(const void* p) { return (unsigned long long)p; }
+static inline double __dadd_rn(double a, double b) { return a + b; }
+static inline double __dsub_rn(double a, double b) { return a - b; }
+static inline double __dmul_rn(double a, double b) { return a * b; }
+// MUFU.RCP64H: the high word of an approximation of 1/d (relative error <= 2^-20, profiles/r1c/exp_rcp.txt); low word zero
+static inline double hb_emu_rcp64h(double d) {
+  double x = 1.0 / d;
+  long long b; std::memcpy(&b, &x, 8);
+  b &= ~0xffffffffLL;
+  std::memcpy(&x, &b, 8);
+  return x;
+}
+using std::exp; using std::log; using std::sqrt; using std::pow; using std::fabs; using std::tan; using std::atan2; using std::fma;
+using std::asin; using std::acos; using std::atan; using std::sinh; using std::cosh; using std::tanh;
+using std::asinh; using std::acosh; using std::atanh; using std::sin; using std::cos;
+#include ENGINE_HEADER
+#include SYS_SOURCE
+typedef SYS_NAME S;
+static constexpr int N = S::N, D = 2 * S::N;
+
+static HbCtx ctx() { HbCtx cx; cx.tab_s = 0; cx.oob = 0; return cx; }
+
+extern "C" void dims(int* o) { o[0] = S::M; o[1] = S::N; o[2] = S::SYMH ? 1 : 0; o[3] = N >= HB_BIG_N ? 1 : 0; }
+
+// hamEqs through the engine's own path (generated derivs/hpre/hpost + hb_spd_solve); returns flag | oob << 8
+extern "C" int ham_eqs(const double* prm, const double* y, double* dy) {
+  double w[S::M];
+  S::inertia(prm, w);
+  HbCtx cx = ctx();
+  int flag = 0;
+  hb_rhs<S, true>(cx, prm, w, y, dy, flag);
+  return flag | (int)(cx.oob << 8);
+}
+extern "C" int rk4_steps(const double* prm, double* y_io, double dt, int nsteps) {
+  double w[S::M];
+  S::inertia(prm, w);
+  HbCtx cx = ctx();
+  int flag = 0;
+  if constexpr (D >= 16) {   // the kernels' large-system path: RK vectors in (emulated) shared memory
+    constexpr int B = HB_BLOCK_OF(S::N);
+    double* sm = hb_rk_smem<D>();
+    for (int c = 0; c < D; c++) sm[c * B] = y_io[c];
+    for (int s = 0; s < nsteps; s++) hb_rk4_step_sm<S, true>(cx, prm, w, sm, dt, dt / 6.0, flag);
+    for (int c = 0; c < D; c++) y_io[c] = sm[c * B];
+  } else {
+    double y[D];
+    for (int c = 0; c < D; c++) y[c] = y_io[c];
+    for (int s = 0; s < nsteps; s++) hb_rk4_step<S, true>(cx, prm, w, y, dt, dt / 6.0, 0.5 * dt, flag);
+    for (int c = 0; c < D; c++) y_io[c] = y[c];
+  }
+  return flag | (int)(cx.oob << 8);
+}
+// stepHam iterated: a fresh GSL-RKF45 solve over (0, dt) per step, exactly as hb_traj_step_rkf45 does
+extern "C" int rkf45_steps(const double* prm, double* y_io, double dt, int nsteps) {
+  double w[S::M];
+  S::inertia(prm, w);
+  HbCtx cx = ctx();
+  int flag = 0;
+  double y[D];
+  for (int c = 0; c < D; c++) y[c] = y_io[c];
+  for (int s = 0; s < nsteps; s++) {
+    HbEvolve<D> e;
+    e.h = dt / 100;
+    e.primed = false;
+    double t = 0.0;
+    hb_rkf45_to<S, true>(cx, prm, w, y, t, dt, e, flag);
+  }
+  for (int c = 0; c < D; c++) y_io[c] = y[c];
+  return flag | (int)(cx.oob << 8);
+}
+// evolveHam over a grid (h and the FSAL derivative carried), as hb_traj_evolve<ADAPTIVE> does; out = s rows of D
+extern "C" int evolve_rkf45(const double* prm, const double* y0, const double* ts, int s, double* out) {
+  double w[S::M];
+  S::inertia(prm, w);
+  HbCtx cx = ctx();
+  int flag = 0;
+  double y[D];
+  for (int c = 0; c < D; c++) y[c] = out[c] = y0[c];
+  HbEvolve<D> e;
+  e.h = (ts[1] - ts[0]) / 100;
+  e.primed = false;
+  double t = ts[0];
+  for (int k = 1; k < s; k++) {
+    hb_rkf45_to<S, true>(cx, prm, w, y, t, ts[k], e, flag);
+    for (int c = 0; c < D; c++) out[k * D + c] = y[c];
+  }
+  return flag | (int)(cx.oob << 8);
+}
+extern "C" int config_maps(const double* prm, const double* q, const double* v, double* p_out, double* v_back, double* U) {
+  double w[S::M];
+  S::inertia(prm, w);
+  HbCtx cx = ctx();
+  int flag = 0;
+  hb_momenta<S, true>(cx, prm, w, q, v, p_out);
+  hb_velocities<S, true, true>(cx, prm, w, q, p_out, v_back, *U, flag);
+  return flag | (int)(cx.oob << 8);
+}
+// primitives
+extern "C" int sincos_fast(double x, double* s, double* c) { HbCtx cx = ctx(); hb_sincos<true>(cx, x, s, c); return (int)cx.oob; }
+extern "C" double rcp_fast(double d) { return hb_rcp(d); }
+template <int NN> static int spd(const double* A_packed, const double* b, double* x) {
+  double A[NN * (NN + 1) / 2];
+  for (int i = 0; i < NN * (NN + 1) / 2; i++) A[i] = A_packed[i];
+  int flag = 0;
+  hb_spd_solve<NN>(A, b, x, flag);
+  return flag;
+}
+extern "C" int spd_solve(int n, const double* A_packed, const double* b, double* x) {
+  switch (n) {
+    case 1: return spd<1>(A_packed, b, x);
+    case 2: return spd<2>(A_packed, b, x);
+    case 3: return spd<3>(A_packed, b, x);
+    case 4: return spd<4>(A_packed, b, x);
+    case 5: return spd<5>(A_packed, b, x);
+    case 7: return spd<7>(A_packed, b, x);
+    case 12: return spd<12>(A_packed, b, x);
+    default: return -1;
+  }
+}

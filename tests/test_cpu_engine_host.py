@@ -1,0 +1,190 @@
+"""The DEVICE engine compiled for the host (tests/host_engine_harness.cpp, HB_HOST_EMU) against the CPU oracle.
+
+The GPU parity suite (-m gpu) is the real gate; this file makes the same code paths — generated hamEqs in both forms,
+the closed-form / LDL^T solves, RK4, the GSL-RKF45 stepper, controller and evolve loop, the table-driven sincos and the
+Newton reciprocal — checkable on a machine without a GPU.  Tolerance as in the GPU suite: 1e-10 per step; the observed
+differences are rounding-level."""
+import ctypes as C
+import os
+import re
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+import hamilton_b200 as hb
+from tests.common import BOXES, maxerr, random_phases
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ENGINE = os.path.join(ROOT, "hamilton_b200", "csrc", "engine", "hb_engine.cuh")
+_dp = C.POINTER(C.c_double)
+NAMES = [n for n in BOXES if n != "chain12"]          # chain12 has its own (slower to compile) test below
+_cache = {}
+
+
+def _p(a):
+    return a.ctypes.data_as(_dp)
+
+
+def harness(name, kind="aot"):
+    """Builds (once per session) the host image of the engine + the generated Sys of a built-in system."""
+    key = (name, kind)
+    if key in _cache:
+        return _cache[key]
+    sid = BOXES[name][0]
+    if kind == "aot":
+        s = hb.systems.builtin(sid)
+    else:
+        os.environ["HB_JIT_SKIP_COMPILE"] = "1"        # symbolic stage only: the host harness compiles the source itself
+        try:
+            s = hb.systems.from_def(hb.systems.DEFS[sid]())
+        finally:
+            del os.environ["HB_JIT_SKIP_COMPILE"]
+    tmp = tempfile.mkdtemp(prefix="hb_hostemu_")
+    src = os.path.join(tmp, "sys.inc")
+    with open(src, "w") as f:
+        f.write(s.source())
+    sname = re.search(r"struct (\w+) \{", s.source()).group(1)
+    so = os.path.join(tmp, "engine_host.so")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", '-DENGINE_HEADER="%s"' % ENGINE,
+                           '-DSYS_SOURCE="%s"' % src, "-DSYS_NAME=" + sname, os.path.join(ROOT, "tests", "host_engine_harness.cpp"), "-o", so])
+    lib = C.CDLL(so)
+    lib.rcp_fast.restype = C.c_double
+    lib.rcp_fast.argtypes = [C.c_double]
+    lib.sincos_fast.argtypes = [C.c_double, _dp, _dp]
+    prm = np.zeros(64)
+    pv = s.params()
+    prm[:len(pv)] = pv
+    _cache[key] = (lib, prm, s)
+    return _cache[key]
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_engine_ham_eqs_and_maps_on_host(name, oracle_mod):
+    lib, prm, s = harness(name)
+    o = oracle_mod.OracleSystem.builtin(BOXES[name][0])
+    n = o.n
+    for y in random_phases(name, 20):
+        dy = np.empty(2 * n)
+        assert lib.ham_eqs(_p(prm), _p(y), _p(dy)) == 0
+        dq, dp = o.ham_eqs(y[:n], y[n:])
+        assert maxerr(dy, np.r_[dq, dp]) < 1e-12
+        v = y[n:].copy()                                   # use the momenta slot as a velocity vector
+        p = np.empty(n); vb = np.empty(n); U = C.c_double()
+        assert lib.config_maps(_p(prm), _p(np.ascontiguousarray(y[:n])), _p(v), _p(p), _p(vb), C.byref(U)) == 0
+        assert maxerr(p, o.momenta(y[:n], v)) < 1e-12 and maxerr(vb, v) < 1e-11 and abs(U.value - o.pe(y[:n])) < 1e-12 * (1 + abs(U.value))
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_engine_rk4_and_rkf45_on_host(name, oracle_mod):
+    lib, prm, s = harness(name)
+    o = oracle_mod.OracleSystem.builtin(BOXES[name][0])
+    ys = random_phases(name, 12)
+    want, bad = o.batch_step(ys, 0, 0.01, 3)
+    assert bad == 0
+    for y, w in zip(ys, want):
+        got = y.copy()
+        assert lib.rk4_steps(_p(prm), _p(got), C.c_double(0.01), 3) == 0
+        assert maxerr(got, w) < 1e-10
+    for dt, k in ((0.01, 2), (1.0 / 12, 3)):              # the second makes the controller work (and reject, for some)
+        want, bad = o.batch_step(ys, 1, dt, k)
+        assert bad == 0
+        for y, w in zip(ys, want):
+            got = y.copy()
+            assert lib.rkf45_steps(_p(prm), _p(got), C.c_double(dt), k) == 0
+            assert maxerr(got, w) < 1e-9
+
+
+def test_engine_rkf45_rejections_and_evolve_on_host(oracle_mod):
+    """The room at the demo's frame step: rejected sub-steps; and an evolveHam grid with h / FSAL carried across rows."""
+    lib, prm, s = harness("room")
+    o = oracle_mod.OracleSystem.builtin(2)
+    q, p = np.array([-1.0, 0.25]), np.array([np.cos(np.pi / 4), np.sin(np.pi / 4)])
+    y = np.r_[q, p]
+    rej = 0
+    for _ in range(60):
+        q, p, st = o.step_ham(1.0 / 12, q, p, stats=True)
+        rej += st.rejects
+        assert lib.rkf45_steps(_p(prm), _p(y), C.c_double(1.0 / 12), 1) == 0
+        assert maxerr(y, np.r_[q, p]) < 1e-9
+        y = np.r_[q, p]                                    # teacher forcing
+    assert rej > 0
+    lib, prm, s = harness("double_pendulum")
+    o = oracle_mod.OracleSystem.builtin(1)
+    y0 = random_phases("double_pendulum", 1)[0]
+    ts = np.linspace(0.0, 1.0, 11)
+    out = np.empty((len(ts), 4))
+    assert lib.evolve_rkf45(_p(prm), _p(y0), _p(ts), len(ts), _p(out)) == 0
+    assert maxerr(out, o.evolve_ham(y0[:2], y0[2:], ts)) < 1e-9
+
+
+def test_engine_jit_source_on_host(oracle_mod):
+    """The tape path (literal parameters, as NVRTC would compile it) through the same harness."""
+    lib, prm, s = harness("triple_pendulum", "jit")
+    o = oracle_mod.OracleSystem.builtin(BOXES["triple_pendulum"][0])
+    for y in random_phases("triple_pendulum", 8):
+        dy = np.empty(6)
+        assert lib.ham_eqs(_p(prm), _p(y), _p(dy)) == 0
+        dq, dp = o.ham_eqs(y[:3], y[3:])
+        assert maxerr(dy, np.r_[dq, dp]) < 1e-12
+
+
+def test_engine_large_system_shared_memory_path_on_host(oracle_mod):
+    """chain12 (n = 12): hpre / parked values / LDL^T / hpost and the shared-memory RK4 the kernels use for n >= 8."""
+    lib, prm, s = harness("chain12")
+    o = oracle_mod.OracleSystem.builtin(BOXES["chain12"][0])
+    ys = random_phases("chain12", 4)
+    for y in ys:
+        dy = np.empty(24)
+        assert lib.ham_eqs(_p(prm), _p(y), _p(dy)) == 0
+        dq, dp = o.ham_eqs(y[:12], y[12:])
+        assert maxerr(dy, np.r_[dq, dp]) < 1e-11
+    want, bad = o.batch_step(ys, 0, 0.01, 2)
+    for y, w in zip(ys, want):
+        got = y.copy()
+        assert lib.rk4_steps(_p(prm), _p(got), C.c_double(0.01), 2) == 0
+        assert maxerr(got, w) < 1e-10
+
+
+def test_fast_sincos_on_host():
+    """hb_sincos<FAST>: 512-entry table + 2-term polynomials; domain |x| < 1e5, everything else flags `oob`."""
+    lib, _, _ = harness("pendulum")
+    rng = np.random.default_rng(7)
+    xs = np.r_[rng.uniform(-np.pi, np.pi, 20000), rng.uniform(-1e5, 1e5, 20000), rng.uniform(-1e-3, 1e-3, 2000),
+               np.arange(-1024, 1025) * (np.pi / 256), [0.0, -0.0, 99999.9, -99999.9, 1e-300]]
+    s, c = C.c_double(), C.c_double()
+    worst = 0.0
+    for x in xs:
+        assert lib.sincos_fast(float(x), C.byref(s), C.byref(c)) == 0
+        worst = max(worst, abs(s.value - np.sin(x)), abs(c.value - np.cos(x)))
+    assert worst < 4e-16
+    for x in (1e5, -1e5, 1e9, float("inf"), float("nan")):
+        assert lib.sincos_fast(x, C.byref(s), C.byref(c)) != 0
+
+
+def test_fast_reciprocal_on_host():
+    """hb_rcp: 20-bit seed (emulated MUFU.RCP64H) + one cubic step: within 1 ulp over the exponent range the solves see."""
+    lib, _, _ = harness("pendulum")
+    rng = np.random.default_rng(11)
+    d = np.exp(rng.uniform(np.log(1e-150), np.log(1e150), 20000)) * rng.choice([-1.0, 1.0], 20000)
+    got = np.array([lib.rcp_fast(float(x)) for x in d])
+    assert np.max(np.abs(got * d - 1.0)) < 2.5e-16
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 7, 12])
+def test_spd_solve_on_host(n):
+    """hb_spd_solve<N>: closed forms for N <= 3, unrolled LDL^T beyond; non-SPD input raises HB_FLAG_NOT_SPD."""
+    lib, _, _ = harness("pendulum")
+    rng = np.random.default_rng(100 + n)
+    for _ in range(50):
+        G = rng.normal(size=(n, n))
+        A = G @ G.T + 0.5 * np.eye(n)
+        b = rng.normal(size=n)
+        packed = np.array([A[j, k] for j in range(n) for k in range(j + 1)])
+        x = np.empty(n)
+        assert lib.spd_solve(n, _p(packed), _p(b), _p(x)) == 0
+        assert np.max(np.abs(x - np.linalg.solve(A, b))) < 1e-11 * np.linalg.cond(A)
+    A = -np.eye(n)
+    packed = np.array([A[j, k] for j in range(n) for k in range(j + 1)])
+    assert lib.spd_solve(n, _p(packed), _p(np.ones(n)), _p(np.empty(n))) & 1
