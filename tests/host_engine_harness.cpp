@@ -14,6 +14,9 @@
 #define __restrict__
 #define __shared__ static
 #define __align__(n)
+#define __global__
+#define __launch_bounds__(...)
+#define __grid_constant__
 struct double2 { double x, y; };
 static inline double2 make_double2(double x, double y) { double2 v; v.x = x; v.y = y; return v; }
 struct HbEmuDim { unsigned x, y, z; };
@@ -141,4 +144,50 @@ extern "C" int spd_solve(int n, const double* A_packed, const double* b, double*
     case 12: return spd<12>(A_packed, b, x);
     default: return -1;
   }
+}
+
+// ---- whole kernels, one emulated thread after another -----------------------------------------------------------------
+// HB_DEFINE_KERNELS gives the nine per-system kernels as ordinary functions hk_<kind>(HbKArgs); run_kernel() walks the
+// (blockIdx, threadIdx) space sequentially — each call runs that thread's whole grid-stride loop, including the prefetch
+// of its next Phase, the out-of-line slow retry and the flag / finite bookkeeping.
+HB_DEFINE_KERNELS(SYS_NAME, hk)
+static void hk_init_random(const HbKArgs a) { hb_body_init_random(a); }
+
+extern "C" int run_kernel(int kid, const double* in, double* out, int* flags, const double* ts, long long n_traj, double dt, int nsteps,
+                          int layout, int s, int substeps, const double* prm, int grid, int block) {
+  HbKArgs a;
+  std::memset(&a, 0, sizeof a);
+  a.in = in; a.out = out; a.flags = flags; a.ts = ts; a.N = n_traj; a.dt = dt; a.dt6 = dt / 6.0; a.dth = 0.5 * dt;
+  a.nsteps = nsteps; a.layout = layout; a.s = s; a.substeps = substeps;
+  for (int k = 0; k < HB_MAXP; k++) a.prm[k] = prm[k];
+  blockDim.x = (unsigned)block; gridDim.x = (unsigned)grid;
+  for (unsigned b = 0; b < (unsigned)grid; b++)
+    for (unsigned t = 0; t < (unsigned)block; t++) {
+      blockIdx.x = b; threadIdx.x = t;
+      switch (kid) {
+        case HB_K_STEP_RK4: hk_step_rk4(a); break;
+        case HB_K_STEP_RKF45: hk_step_rkf45(a); break;
+        case HB_K_EVOLVE_RK4: hk_evolve_rk4(a); break;
+        case HB_K_EVOLVE_RKF45: hk_evolve_rkf45(a); break;
+        case HB_K_HAM_EQS: hk_ham_eqs(a); break;
+        case HB_K_TO_PHASE: hk_to_phase(a); break;
+        case HB_K_FROM_PHASE: hk_from_phase(a); break;
+        case HB_K_ENERGIES: hk_energies(a); break;
+        case HB_K_UPOS: hk_upos(a); break;
+        default: return -1;
+      }
+    }
+  blockIdx.x = threadIdx.x = 0; blockDim.x = 128; gridDim.x = 1;
+  return 0;
+}
+extern "C" void run_init_random(double* out, long long n_traj, int d, int layout, unsigned long long seed, long long first,
+                                const double* lo, const double* hi, int grid, int block) {
+  HbKArgs a;
+  std::memset(&a, 0, sizeof a);
+  a.out = out; a.N = n_traj; a.nsteps = d; a.layout = layout; a.seed = seed; a.first = first;
+  for (int c = 0; c < d; c++) { a.prm[c] = lo[c]; a.prm[d + c] = hi[c]; }
+  blockDim.x = (unsigned)block; gridDim.x = (unsigned)grid;
+  for (unsigned b = 0; b < (unsigned)grid; b++)
+    for (unsigned t = 0; t < (unsigned)block; t++) { blockIdx.x = b; threadIdx.x = t; hk_init_random(a); }
+  blockIdx.x = threadIdx.x = 0; blockDim.x = 128; gridDim.x = 1;
 }

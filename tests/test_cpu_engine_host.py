@@ -188,3 +188,116 @@ def test_spd_solve_on_host(n):
     A = -np.eye(n)
     packed = np.array([A[j, k] for j in range(n) for k in range(j + 1)])
     assert lib.spd_solve(n, _p(packed), _p(np.ones(n)), _p(np.empty(n))) & 1
+
+
+# ---- whole kernels on the host: the grid-stride bodies, layouts, flags, the slow retry, init_random ---------------------
+K_STEP_RK4, K_STEP_RKF45, K_EVOLVE_RK4, K_EVOLVE_RKF45, K_HAM_EQS, K_TO_PHASE, K_FROM_PHASE, K_ENERGIES, K_UPOS = range(9)
+AOS, SOA = 0, 1
+
+
+def run_kernel(lib, prm, kid, inp, out, N, dt=0.0, nsteps=1, layout=AOS, flags=None, ts=None, substeps=1, grid=3, block=128):
+    tsp = _p(ts) if ts is not None else None
+    fl = flags.ctypes.data_as(C.POINTER(C.c_int32)) if flags is not None else None
+    rc = lib.run_kernel(kid, _p(inp), _p(out), fl, tsp, C.c_longlong(N), C.c_double(dt), nsteps, layout, 0 if ts is None else len(ts),
+                        substeps, _p(prm), grid, block)
+    assert rc == 0
+
+
+@pytest.mark.parametrize("name", ["double_pendulum", "pendulum", "spring", "chain12"])
+@pytest.mark.parametrize("layout", [AOS, SOA])
+def test_kernel_bodies_step_on_host(name, layout, oracle_mod):
+    """step_rk4 / step_rkf45 kernels, 3 CTAs x 128 emulated threads over a ragged batch (every thread walks several
+    trajectories with the prefetch of the next Phase), both layouts, out of place and in place."""
+    lib, prm, s = harness(name)
+    o = oracle_mod.OracleSystem.builtin(BOXES[name][0])
+    N = 70 if name == "chain12" else 1000
+    y = random_phases(name, N)
+    d = y.shape[1]
+    for kid, integ, steps, tol in ((K_STEP_RK4, 0, 2, 1e-10), (K_STEP_RKF45, 1, 1, 1e-9)):
+        if name == "chain12" and kid == K_STEP_RKF45:
+            continue
+        want, bad = o.batch_step(y, integ, 0.01, steps)
+        assert bad == 0
+        yin = np.ascontiguousarray(y.T) if layout == SOA else y.copy()
+        out = np.full_like(yin, np.nan)
+        fl = np.zeros(N, np.int32)
+        run_kernel(lib, prm, kid, yin, out, N, dt=0.01, nsteps=steps, layout=layout, flags=fl, grid=1 if name == "chain12" else 3)
+        got = out.T if layout == SOA else out
+        assert maxerr(got, want) < tol * steps and not fl.any()
+        run_kernel(lib, prm, kid, yin, yin, N, dt=0.01, nsteps=steps, layout=layout, grid=2)      # in place
+        assert np.array_equal(yin, out)
+
+
+def test_kernel_bodies_other_entry_points_on_host(oracle_mod):
+    lib, prm, s = harness("double_pendulum")
+    o = oracle_mod.OracleSystem.builtin(1)
+    N, n, m = 300, 2, 4
+    y = random_phases("double_pendulum", N)
+    out = np.empty_like(y)
+    run_kernel(lib, prm, K_HAM_EQS, y, out, N)
+    for i in (0, 17, 299):
+        dq, dp = o.ham_eqs(y[i, :n], y[i, n:])
+        assert maxerr(out[i], np.r_[dq, dp]) < 1e-12
+    cfg = y.copy()                                          # read as Config [q, v]
+    ph = np.empty_like(y)
+    run_kernel(lib, prm, K_TO_PHASE, cfg, ph, N)
+    back = np.empty_like(y)
+    run_kernel(lib, prm, K_FROM_PHASE, ph, back, N)
+    assert maxerr(back, cfg) < 1e-11
+    for i in (3, 150):
+        assert maxerr(ph[i, n:], o.momenta(cfg[i, :n], cfg[i, n:])) < 1e-12
+    en = np.empty((N, 4))
+    run_kernel(lib, prm, K_ENERGIES, y, en, N)
+    for i in (5, 250):
+        T, U = o.keP(y[i, :n], y[i, n:]), o.pe(y[i, :n])
+        assert maxerr(en[i], np.array([T, U, T + U, T - U])) < 1e-12
+    q = np.ascontiguousarray(y[:, :n])
+    x = np.empty((N, m))
+    run_kernel(lib, prm, K_UPOS, q, x, N)
+    assert maxerr(x[7], o.underlying_pos(q[7])) < 1e-13
+    # evolve: s rows of the batch, first row = initial state, RK4 sub-steps or GSL-RKF45 carried across rows
+    ts = np.linspace(0.0, 0.3, 4)
+    rows = np.empty((len(ts),) + y.shape)
+    run_kernel(lib, prm, K_EVOLVE_RKF45, y, rows, N, ts=ts)
+    assert np.array_equal(rows[0], y)
+    for i in (0, 123):
+        assert maxerr(rows[:, i, :], o.evolve_ham(y[i, :n], y[i, n:], ts)) < 1e-9
+    run_kernel(lib, prm, K_EVOLVE_RK4, y, rows, N, ts=ts, substeps=5)
+    want, _ = o.batch_step(y, 0, 0.02, 5)                  # 0.1 per row = 5 sub-steps of 0.02
+    assert maxerr(rows[1], want) < 1e-10
+
+
+def test_kernel_flags_and_slow_retry_on_host(oracle_mod):
+    """Singular mass matrices raise HB_FLAG_NOT_SPD for exactly those trajectories (OR-ed into the caller's flags);
+    angles outside the fast sincos domain are redone out of line with libm and still match the oracle, in place too."""
+    lib, prm, s = harness("two_body")
+    y = random_phases("two_body", 200)
+    y[5, 0] = 0.0
+    y[-1, 0] = 0.0                                          # r = 0
+    fl = np.zeros(200, np.int32)
+    fl[7] = 64
+    out = np.empty_like(y)
+    run_kernel(lib, prm, K_STEP_RK4, y, out, 200, dt=0.01, flags=fl)
+    assert sorted(np.nonzero(fl)[0].tolist()) == [5, 7, 199] and fl[7] == 64 and fl[5] != 0
+    lib, prm, s = harness("double_pendulum")
+    o = oracle_mod.OracleSystem.builtin(1)
+    y = random_phases("double_pendulum", 64)
+    y[3, 0] += 2e5
+    y[40, 1] -= 7e7
+    want, bad = o.batch_step(y, 0, 0.01, 2)
+    assert bad == 0
+    buf = y.copy()
+    run_kernel(lib, prm, K_STEP_RK4, buf, buf, 64, dt=0.01, nsteps=2, grid=1)
+    assert maxerr(buf, want) < 1e-10 * 2
+
+
+@pytest.mark.parametrize("layout", [AOS, SOA])
+def test_init_random_kernel_on_host_is_bit_identical(layout, oracle_mod):
+    lib, prm, s = harness("double_pendulum")
+    o = oracle_mod.OracleSystem.builtin(1)
+    lo, hi = [np.array(v, dtype=float) for v in BOXES["double_pendulum"][1:]]
+    N, first = 777, 1 << 20
+    out = np.empty((N, 4) if layout == AOS else (4, N))
+    lib.run_init_random(_p(out), C.c_longlong(N), 4, layout, C.c_ulonglong(0x48414D49), C.c_longlong(first), _p(lo), _p(hi), 2, 128)
+    want = o.init_random(0x48414D49, first, N, lo, hi)
+    assert np.array_equal(out if layout == AOS else out.T, want)
