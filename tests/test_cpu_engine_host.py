@@ -27,9 +27,9 @@ def _p(a):
     return a.ctypes.data_as(_dp)
 
 
-def harness(name, kind="aot"):
+def harness(name, kind="aot", defines=()):
     """Builds (once per session) the host image of the engine + the generated Sys of a built-in system."""
-    key = (name, kind)
+    key = (name, kind, tuple(defines))
     if key in _cache:
         return _cache[key]
     sid = BOXES[name][0]
@@ -47,7 +47,7 @@ def harness(name, kind="aot"):
         f.write(s.source())
     sname = re.search(r"struct (\w+) \{", s.source()).group(1)
     so = os.path.join(tmp, "engine_host.so")
-    subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", '-DENGINE_HEADER="%s"' % ENGINE,
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off"] + ["-D" + d for d in defines] + ['-DENGINE_HEADER="%s"' % ENGINE,
                            '-DSYS_SOURCE="%s"' % src, "-DSYS_NAME=" + sname, os.path.join(ROOT, "tests", "host_engine_harness.cpp"), "-o", so])
     lib = C.CDLL(so)
     lib.rcp_fast.restype = C.c_double
@@ -301,3 +301,23 @@ def test_init_random_kernel_on_host_is_bit_identical(layout, oracle_mod):
     lib.run_init_random(_p(out), C.c_longlong(N), 4, layout, C.c_ulonglong(0x48414D49), C.c_longlong(first), _p(lo), _p(hi), 2, 128)
     want = o.init_random(0x48414D49, first, N, lo, hi)
     assert np.array_equal(out if layout == AOS else out.T, want)
+
+
+@pytest.mark.parametrize("defines", [("HB_UNROLL2=1",), ("HB_L2_PREFETCH=1",), ("HB_LAYSPEC=0",), ("HB_SR_2OP=1", "HB_SC_LITERALS=1")])
+def test_engine_experiment_switches_keep_results_on_host(defines, oracle_mod):
+    """The compile-time experiment switches of the engine (profiles/ A/Bs, round-2 candidates) must not change results:
+    same kernels, same ragged batch, against the oracle."""
+    lib, prm, s = harness("double_pendulum", defines=defines)
+    o = oracle_mod.OracleSystem.builtin(1)
+    N = 901
+    y = random_phases("double_pendulum", N)
+    y[11, 0] += 3e5                                        # one trajectory through the slow retry
+    for layout in (AOS, SOA):
+        want, bad = o.batch_step(y, 0, 0.01, 2)
+        assert bad == 0
+        yin = np.ascontiguousarray(y.T) if layout == SOA else y.copy()
+        out = np.full_like(yin, np.nan)
+        run_kernel(lib, prm, K_STEP_RK4, yin, out, N, dt=0.01, nsteps=2, layout=layout, grid=2)
+        assert maxerr(out.T if layout == SOA else out, want) < 2e-10
+        run_kernel(lib, prm, K_STEP_RK4, yin, yin, N, dt=0.01, nsteps=2, layout=layout, grid=3)
+        assert np.array_equal(yin, out)
