@@ -21,6 +21,7 @@ ENGINE = os.path.join(ROOT, "hamilton_b200", "csrc", "engine", "hb_engine.cuh")
 _dp = C.POINTER(C.c_double)
 NAMES = [n for n in BOXES if n != "chain12"]          # chain12 has its own (slower to compile) test below
 _cache = {}
+_tmpdirs = []
 
 
 def _p(a):
@@ -41,7 +42,9 @@ def harness(name, kind="aot", defines=()):
             s = hb.systems.from_def(hb.systems.DEFS[sid]())
         finally:
             del os.environ["HB_JIT_SKIP_COMPILE"]
-    tmp = tempfile.mkdtemp(prefix="hb_hostemu_")
+    holder = tempfile.TemporaryDirectory(prefix="hb_hostemu_")   # removed when the test session's cache is dropped
+    _tmpdirs.append(holder)
+    tmp = holder.name
     src = os.path.join(tmp, "sys.inc")
     with open(src, "w") as f:
         f.write(s.source())
