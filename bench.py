@@ -365,7 +365,7 @@ def main():
             "clocks": clocks,
             "gpu_launches": args.steps,
             "e2e": {"value": world * N * e2e_steps / (e2e_ms * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": N * 32, "d2h_bytes_per_step": N * 32,
-                    "steps": e2e_steps, "call": "hb_batch_step(HB_INTEG_RK4, nsteps=1, HB_MEM_HOST) on pinned host arrays, blocking",
+                    "steps": e2e_steps, "call": "hb_batch_step(HB_INTEG_RK4, nsteps=1, HB_MEM_HOST) on pinned host arrays, blocking: one kernel reads the Phases from and writes the results to host memory over PCIe (DESIGN.md section 2)",
                     "host_binding": numa},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "kernel": "hbk_double_pendulum_dflt_step_rk4",
