@@ -29,7 +29,7 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-os.environ.setdefault("HB_JIT_CACHE_DIR", os.path.join(ROOT, ".jit_cache"))   # NVRTC output cache stays inside the repository
+os.environ.setdefault("HB_JIT_CACHE_DIR", os.path.join(ROOT, ".jit_cache", "gpu" if os.path.exists("/dev/nvidiactl") else "cpu"))   # NVRTC output cache stays inside the repository
 sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402

@@ -9,7 +9,7 @@ if ROOT not in sys.path:
 
 
 # NVRTC output of tape systems is cached on disk (csrc/runtime.cpp); keep the cache inside the repository for test runs
-os.environ.setdefault("HB_JIT_CACHE_DIR", os.path.join(ROOT, ".jit_cache"))
+os.environ.setdefault("HB_JIT_CACHE_DIR", os.path.join(ROOT, ".jit_cache", "gpu" if os.path.exists("/dev/nvidiactl") else "cpu"))
 
 
 def pytest_configure(config):
