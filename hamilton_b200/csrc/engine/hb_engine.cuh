@@ -35,7 +35,10 @@
 #define HB_MAXP 64
 // Threads per CTA, fixed per system size (the host launches exactly this): 128 for small systems whose whole
 // state lives in registers and for n >= 8, where the RK vectors are staged in dynamic shared memory (HB_DYN_DOUBLES).
-#define HB_BLOCK_OF(NCOORD) 128
+#ifndef HB_BLOCK_SMALL
+#define HB_BLOCK_SMALL 128   // CTA size of small systems (A/B switch; the host launches what HB_BLOCK says, <= this)
+#endif
+#define HB_BLOCK_OF(NCOORD) ((NCOORD) >= HB_BIG_N ? 128 : HB_BLOCK_SMALL)
 // Large systems (n >= HB_BIG_N) keep the RK4 vectors (y, acc, stage input: 3 * 2n doubles per thread) and, for
 // symbolically compiled systems, the values hpre hands to hpost (NE doubles per thread) in DYNAMIC shared memory,
 // column per thread (conflict-free), so that the registers are left to the mass matrix and its factor.
@@ -77,38 +80,40 @@ struct HbKArgs {
 };
 
 // ---------------------------------------------------------------------------- batch I/O ----
-template <int D>
-HB_DEV void hb_load(const double* __restrict__ base, long long i, long long N, int layout, double (&y)[D]) {
+// I = index type: `unsigned` in the kernels (a launch holds < 2^31 trajectories, so i * D * 8 is ONE IMAD.WIDE.U32 instead
+// of a 64-bit multiply-add chain), `long long` in the out-of-line slow path.
+template <int D, class I>
+HB_DEV void hb_load(const double* __restrict__ base, I i, I N, int layout, double (&y)[D]) {
   if (layout != 1) {
     if constexpr (D % 2 == 0) {   // 16-byte vector loads: a Phase is 2n doubles, always even
-      const double2* p = reinterpret_cast<const double2*>(base + i * D);
+      const double2* p = reinterpret_cast<const double2*>(base + (size_t)i * D);
 #pragma unroll
       for (int c = 0; c < D / 2; c++) { double2 v = p[c]; y[2 * c] = v.x; y[2 * c + 1] = v.y; }
     } else {
 #pragma unroll
-      for (int c = 0; c < D; c++) y[c] = base[i * D + c];
+      for (int c = 0; c < D; c++) y[c] = base[(size_t)i * D + c];
     }
   } else {
 #pragma unroll
-    for (int c = 0; c < D; c++) y[c] = base[(long long)c * N + i];   // one coalesced stream per component
+    for (int c = 0; c < D; c++) y[c] = base[(size_t)c * N + i];   // one coalesced stream per component
   }
 }
 // layout 2 (internal; set by the host when `out` is page-locked HOST memory written in place over PCIe): array of Phases
 // like layout 0, but a warp transposes its 32 Phases through shared memory so that every store instruction writes 512
 // contiguous bytes.  A thread-per-Phase store (16 bytes at a 2n*8-byte stride) reaches the host as partial-sector
 // writes: 12.7 GB/s measured against 53.6 GB/s for the transposed form (profiles/r1h/zc.txt).
-template <int D>
-HB_DEV void hb_store(double* __restrict__ base, long long i, long long N, int layout, const double (&y)[D]) {
+template <int D, class I>
+HB_DEV void hb_store(double* __restrict__ base, I i, I N, int layout, const double (&y)[D]) {
   if constexpr (D % 2 == 0 && D <= HB_WSTORE_MAXD) {
     if (layout == 2) {
       if (__activemask() == 0xffffffffu) {   // whole warp here together: lanes hold 32 consecutive trajectories
-        __shared__ double2 xp[HB_BLOCK_OF(D / 2) * (D / 2)];
+        __shared__ double2 xp[HB_MAXBLOCK_OF(D / 2) * (D / 2)];
         const int lane = threadIdx.x & 31;
         double2* w = xp + (threadIdx.x - lane) * (D / 2);
 #pragma unroll
         for (int c = 0; c < D / 2; c++) w[lane * (D / 2) + c] = make_double2(y[2 * c], y[2 * c + 1]);
         __syncwarp();
-        double2* g = reinterpret_cast<double2*>(base + (i - lane) * D);
+        double2* g = reinterpret_cast<double2*>(base + (size_t)(i - lane) * D);
 #pragma unroll
         for (int k = 0; k < D / 2; k++) g[32 * k + lane] = w[32 * k + lane];
         __syncwarp();
@@ -119,34 +124,35 @@ HB_DEV void hb_store(double* __restrict__ base, long long i, long long N, int la
   }
   if (layout != 1) {
     if constexpr (D % 2 == 0) {
-      double2* p = reinterpret_cast<double2*>(base + i * D);
+      double2* p = reinterpret_cast<double2*>(base + (size_t)i * D);
 #pragma unroll
       for (int c = 0; c < D / 2; c++) p[c] = make_double2(y[2 * c], y[2 * c + 1]);
     } else {
 #pragma unroll
-      for (int c = 0; c < D; c++) base[i * D + c] = y[c];
+      for (int c = 0; c < D; c++) base[(size_t)i * D + c] = y[c];
     }
   } else {
 #pragma unroll
-    for (int c = 0; c < D; c++) base[(long long)c * N + i] = y[c];
+    for (int c = 0; c < D; c++) base[(size_t)c * N + i] = y[c];
   }
 }
-#ifndef HB_L2_PREFETCH
-#define HB_L2_PREFETCH 0   // 1: the next Phase is prefetched into L2 (no registers held across the step) instead of into registers
+// L2 prefetch of one trajectory's input record (every 32-byte sector of it).  A prefetch into L2 — the memory-side cache,
+// the point of coherence — can never make stale data visible, so the kernels issue it for their first two rounds BEFORE
+// griddepcontrol.wait: the DRAM latency of the first loads hides under the previous kernel's tail.
+#ifndef HB_PRE_L2
+#define HB_PRE_L2 1
 #endif
-#ifndef HB_L2_AHEAD
-#define HB_L2_AHEAD 0      // k > 0: besides the register prefetch of the next Phase, pull the Phase k iterations further into L2
-#endif
-template <int D>
-HB_DEV void hb_prefetch_l2(const double* base, long long i, long long N, int layout) {
+template <int D, class I>
+HB_DEV void hb_prefetch_l2(const double* base, I i, I N, int layout) {
 #ifdef HB_HOST_EMU
   (void)base; (void)i; (void)N; (void)layout;
 #else
   if (layout != 1) {
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(base + i * D));
+#pragma unroll
+    for (int c = 0; c < D; c += 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)i * D + c));
   } else {
 #pragma unroll
-    for (int c = 0; c < D; c++) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (long long)c * N + i));
+    for (int c = 0; c < D; c++) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)c * N + i));
   }
 #endif
 }
@@ -161,6 +167,17 @@ HB_DEV bool hb_finite(double x) { return (__double2hiint(x) & 0x7ff00000) != 0x7
 #define HB_PDL_LAUNCH_DEPENDENTS() asm volatile("griddepcontrol.launch_dependents;")
 #define HB_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
 #endif
+// Shared-window address of a shared-memory object, computed ONCE: the volatile asm keeps ptxas from rematerialising the
+// generic->shared conversion (S2R SR_CgaCtaId + MOV + LEA) in front of every use inside the trajectory loop.
+HB_DEV unsigned hb_smem_addr(const void* p) {
+#ifdef HB_HOST_EMU
+  (void)p; return 0u;
+#else
+  unsigned r;
+  asm volatile("{\n\t.reg .u64 t;\n\tcvta.to.shared.u64 t, %1;\n\tcvt.u32.u64 %0, t;\n\t}" : "=r"(r) : "l"(p));
+  return r;
+#endif
+}
 #ifdef HB_HOST_EMU
 static double hb_dsm[1 << 17];
 HB_DEV double hb_lds(const double* p) { return *p; }
@@ -183,393 +200,98 @@ HB_DEV void hb_copy(const double* src, double (&dst)[D]) {
 }
 
 // ------------------------------------------------------------------------ fp64 primitives --
-// The FP64 pipe (64 FMA/clk/SM) and the issue slots are what bound this engine, so the two
-// transcendental-class primitives every mechanical system leans on are hand-written.
+// On B200 an FP64 instruction keeps a scheduler's issue port for 2 clocks (3 with three distinct register operands) and
+// every other instruction costs one more issue clock on top (profiles/r2a/fp64_issue_model.txt), so the engine is bound
+// by the TOTAL instruction count of a step, FP64 instructions weighing double.  The two transcendental-class primitives
+// every mechanical system leans on are therefore hand-written, and their bookkeeping counted instruction by instruction.
 //
-// hb_sincos<FAST=true>: x = k*(pi/64) + r with k = rint(x*64/pi) obtained from the 1.5*2^52 magic
-// constant (no F2I/I2F), two-term Cody-Waite reduction, |r| <= pi/128; (sin, cos)(k*pi/64) come from
-// a 128-entry table staged in shared memory (one LDS.128), sin r and cos r - 1 from 3-term
-// polynomials, combined by the angle-addition formulas: 16 DFMA-class instructions instead of the
-// ~24 + ~28 immediate-materialising moves of libdevice's sincos, no quadrant logic, no branch.
-// Arguments with |x| >= 1e5 (or non-finite) only set cx.oob; the caller then redoes that
+// hb_sincos<FAST=true>: x = k * (2 pi / HB_SC_N) + r with k = rint(x * HB_SC_N / 2 pi) obtained from the magic constant
+// 1.5 * 2^52 + 2^31 (no F2I/I2F; the 2^31 bias keeps the low word of t = fma(x, HB_SC_N / 2 pi, magic) non-negative, so
+// "argument in the domain" is hi(t) == 0x43380000: ONE LOP3 accumulates the domain check);  (sin, cos)(k 2 pi / HB_SC_N)
+// come from a 2048-entry table staged in shared memory (one LDS.128, address = LOP3 + IMAD);  |r| <= pi / 2048, so
+// sin r = r + r^3 S1' (one minimax term, truncation error 9e-18) and cos r - 1 = z (C1 + z C2); angle-addition
+// recombination: 12 FP64 instructions + 4 others, no branch, no quadrant logic (libdevice sincos: ~24 FP64 + ~28 others).
+// Reduction: one FMA against fp64(2 pi / HB_SC_N) — the product is exact inside the FMA, the constant's own rounding
+// error (3.9e-17 relative) makes the result sin/cos of x (1 + 3.9e-17): a perturbation of 0.36 ulp of the ARGUMENT, below
+// the 0.5 ulp the argument already carries from the RK stage update that produced it.  Max abs error
+// 2.5e-16 + 3.9e-17 |x| (checked against mpmath / long double on the host, tests/test_cpu_engine_host.py);
+// HB_SC_CW2=1 restores the two-term Cody-Waite reduction (error 2.5e-16 over the whole domain, +1 DFMA per sincos).
+// Arguments with |x| >= 2^31 * 2 pi / HB_SC_N (6.6e6; or non-finite) only set cx.oob; the caller then redoes that
 // trajectory on the out-of-line slow path (FAST=false: libdevice sincos with Payne-Hanek reduction).
-// Max abs error of the fast path ~2e-16 (checked against long double on the host).
 struct HbCtx {
-  unsigned tab_s;       // shared-window address of the staged hb_kSinCosTab (fast path only)
-  unsigned oob;         // set when a fast-path primitive saw an argument outside its domain
+  unsigned tab_s;       // shared-window address of the staged sin/cos table (fast path only)
+  unsigned oob;         // non-zero when a fast-path primitive saw an argument outside its domain
+  int minpiv;           // smallest high word of any mass-matrix pivot seen (hb_bad_pivot test deferred to the end)
 };
+HB_DEV void hb_ctx_reset(HbCtx& cx) { cx.oob = 0; cx.minpiv = 0x7fffffff; }
 
+#include "hb_sincos_tab.cuh"   // hb_kSinCosTab[2048] = {sin, cos}(k pi / 1024), correctly rounded (gen_sincos_tab.py)
 #ifndef HB_SC_LOG2
-#define HB_SC_LOG2 9          // table of 2^HB_SC_LOG2 entries over the full circle (7: 2 KB, 3+3 polynomial terms; 9: 8 KB, 2+2)
+#define HB_SC_LOG2 11         // staged entries over the full circle: 11 = the whole table (32 KB), 9 = every 4th entry (8 KB)
+#endif
+#ifndef HB_SC_CW2
+#define HB_SC_CW2 0           // 1: two-term Cody-Waite reduction
 #endif
 #define HB_SC_N (1 << HB_SC_LOG2)
-// The table is staged HB_SC_REP times, entry k of copy r at [k * HB_SC_REP + r]; lane l reads copy l % HB_SC_REP.  An
-// LDS.128 is served a quarter-warp (8 lanes x 16 bytes) per wavefront, and with data-dependent k a single copy costs
-// 10.3 wavefronts per load instead of 4 (ncu source page, profiles/r1e): the copies pin lanes to disjoint bank groups.
-#ifndef HB_SC_REP_LOG2
-#define HB_SC_REP_LOG2 0
-#endif
-#define HB_SC_REP (1 << HB_SC_REP_LOG2)
-#if HB_SC_LOG2 == 7
-static __device__ const double2 hb_kSinCosTab[HB_SC_N] = {   // {sin, cos}(k*pi/64), correctly rounded
-    {0, 1}, {0.049067674327418015, 0.99879545620517241},
-    {0.098017140329560604, 0.99518472667219693}, {0.14673047445536175, 0.98917650996478101},
-    {0.19509032201612828, 0.98078528040323043}, {0.2429801799032639, 0.97003125319454397},
-    {0.29028467725446239, 0.95694033573220882}, {0.33688985339222005, 0.94154406518302081},
-    {0.38268343236508978, 0.92387953251128674}, {0.42755509343028208, 0.90398929312344334},
-    {0.47139673682599764, 0.88192126434835505}, {0.51410274419322177, 0.85772861000027212},
-    {0.55557023301960218, 0.83146961230254524}, {0.59569930449243336, 0.80320753148064494},
-    {0.63439328416364549, 0.77301045336273699}, {0.67155895484701844, 0.74095112535495911},
-    {0.70710678118654757, 0.70710678118654757}, {0.74095112535495911, 0.67155895484701844},
-    {0.77301045336273699, 0.63439328416364549}, {0.80320753148064494, 0.59569930449243336},
-    {0.83146961230254524, 0.55557023301960218}, {0.85772861000027212, 0.51410274419322177},
-    {0.88192126434835505, 0.47139673682599764}, {0.90398929312344334, 0.42755509343028208},
-    {0.92387953251128674, 0.38268343236508978}, {0.94154406518302081, 0.33688985339222005},
-    {0.95694033573220882, 0.29028467725446239}, {0.97003125319454397, 0.2429801799032639},
-    {0.98078528040323043, 0.19509032201612828}, {0.98917650996478101, 0.14673047445536175},
-    {0.99518472667219693, 0.098017140329560604}, {0.99879545620517241, 0.049067674327418015},
-    {1, 0}, {0.99879545620517241, -0.049067674327418015},
-    {0.99518472667219693, -0.098017140329560604}, {0.98917650996478101, -0.14673047445536175},
-    {0.98078528040323043, -0.19509032201612828}, {0.97003125319454397, -0.2429801799032639},
-    {0.95694033573220882, -0.29028467725446239}, {0.94154406518302081, -0.33688985339222005},
-    {0.92387953251128674, -0.38268343236508978}, {0.90398929312344334, -0.42755509343028208},
-    {0.88192126434835505, -0.47139673682599764}, {0.85772861000027212, -0.51410274419322177},
-    {0.83146961230254524, -0.55557023301960218}, {0.80320753148064494, -0.59569930449243336},
-    {0.77301045336273699, -0.63439328416364549}, {0.74095112535495911, -0.67155895484701844},
-    {0.70710678118654757, -0.70710678118654757}, {0.67155895484701844, -0.74095112535495911},
-    {0.63439328416364549, -0.77301045336273699}, {0.59569930449243336, -0.80320753148064494},
-    {0.55557023301960218, -0.83146961230254524}, {0.51410274419322177, -0.85772861000027212},
-    {0.47139673682599764, -0.88192126434835505}, {0.42755509343028208, -0.90398929312344334},
-    {0.38268343236508978, -0.92387953251128674}, {0.33688985339222005, -0.94154406518302081},
-    {0.29028467725446239, -0.95694033573220882}, {0.2429801799032639, -0.97003125319454397},
-    {0.19509032201612828, -0.98078528040323043}, {0.14673047445536175, -0.98917650996478101},
-    {0.098017140329560604, -0.99518472667219693}, {0.049067674327418015, -0.99879545620517241},
-    {0, -1}, {-0.049067674327418015, -0.99879545620517241},
-    {-0.098017140329560604, -0.99518472667219693}, {-0.14673047445536175, -0.98917650996478101},
-    {-0.19509032201612828, -0.98078528040323043}, {-0.2429801799032639, -0.97003125319454397},
-    {-0.29028467725446239, -0.95694033573220882}, {-0.33688985339222005, -0.94154406518302081},
-    {-0.38268343236508978, -0.92387953251128674}, {-0.42755509343028208, -0.90398929312344334},
-    {-0.47139673682599764, -0.88192126434835505}, {-0.51410274419322177, -0.85772861000027212},
-    {-0.55557023301960218, -0.83146961230254524}, {-0.59569930449243336, -0.80320753148064494},
-    {-0.63439328416364549, -0.77301045336273699}, {-0.67155895484701844, -0.74095112535495911},
-    {-0.70710678118654757, -0.70710678118654757}, {-0.74095112535495911, -0.67155895484701844},
-    {-0.77301045336273699, -0.63439328416364549}, {-0.80320753148064494, -0.59569930449243336},
-    {-0.83146961230254524, -0.55557023301960218}, {-0.85772861000027212, -0.51410274419322177},
-    {-0.88192126434835505, -0.47139673682599764}, {-0.90398929312344334, -0.42755509343028208},
-    {-0.92387953251128674, -0.38268343236508978}, {-0.94154406518302081, -0.33688985339222005},
-    {-0.95694033573220882, -0.29028467725446239}, {-0.97003125319454397, -0.2429801799032639},
-    {-0.98078528040323043, -0.19509032201612828}, {-0.98917650996478101, -0.14673047445536175},
-    {-0.99518472667219693, -0.098017140329560604}, {-0.99879545620517241, -0.049067674327418015},
-    {-1, 0}, {-0.99879545620517241, 0.049067674327418015},
-    {-0.99518472667219693, 0.098017140329560604}, {-0.98917650996478101, 0.14673047445536175},
-    {-0.98078528040323043, 0.19509032201612828}, {-0.97003125319454397, 0.2429801799032639},
-    {-0.95694033573220882, 0.29028467725446239}, {-0.94154406518302081, 0.33688985339222005},
-    {-0.92387953251128674, 0.38268343236508978}, {-0.90398929312344334, 0.42755509343028208},
-    {-0.88192126434835505, 0.47139673682599764}, {-0.85772861000027212, 0.51410274419322177},
-    {-0.83146961230254524, 0.55557023301960218}, {-0.80320753148064494, 0.59569930449243336},
-    {-0.77301045336273699, 0.63439328416364549}, {-0.74095112535495911, 0.67155895484701844},
-    {-0.70710678118654757, 0.70710678118654757}, {-0.67155895484701844, 0.74095112535495911},
-    {-0.63439328416364549, 0.77301045336273699}, {-0.59569930449243336, 0.80320753148064494},
-    {-0.55557023301960218, 0.83146961230254524}, {-0.51410274419322177, 0.85772861000027212},
-    {-0.47139673682599764, 0.88192126434835505}, {-0.42755509343028208, 0.90398929312344334},
-    {-0.38268343236508978, 0.92387953251128674}, {-0.33688985339222005, 0.94154406518302081},
-    {-0.29028467725446239, 0.95694033573220882}, {-0.2429801799032639, 0.97003125319454397},
-    {-0.19509032201612828, 0.98078528040323043}, {-0.14673047445536175, 0.98917650996478101},
-    {-0.098017140329560604, 0.99518472667219693}, {-0.049067674327418015, 0.99879545620517241},
-};
-static __device__ __constant__ double hb_kSC[10] = {
-    20.371832715762604,           // 0  64/pi
-    6755399441055744.0,           // 1  1.5 * 2^52
-    0.04908738521234052,          // 2  pi/64 hi
-    1.9135106236677394e-18,       // 3  pi/64 lo
-    -1.0 / 6.0, 1.0 / 120.0, -1.0 / 5040.0,      // 4..6   sin r = r + r^3 (S1 + z (S2 + z S3))
-    -0.5, 1.0 / 24.0, -1.0 / 720.0};             // 7..9   cos r - 1 = z (C1 + z (C2 + z C3))
+#define HB_SC_MAGIC 6755401588539392.0   // 1.5 * 2^52 + 2^31
+// The constants sit in the constant bank so that they are DIRECT operands of the FP64 instructions (written as literals
+// ptxas rebuilds each one in a register pair per trajectory: 18 extra issue slots per RK4 step of the double pendulum).
+#if HB_SC_LOG2 == 11
+static __device__ __constant__ double hb_kSC[5] = {
+    325.94932345220167,        // 0  1024 / pi
+    0.0030679615757712823,     // 1  pi / 1024 (fp64)
+    1.195944139792337e-19,     // 2  pi / 1024 - fp64(pi / 1024)
+    -0.16666664960671299,      // 3  S1' = -1/6 + 0.87 zmax / 120: minimax for sin r = r + r^3 S1' over |r| <= pi/2048
+    0.0};
+#elif HB_SC_LOG2 == 9
+static __device__ __constant__ double hb_kSC[5] = {
+    81.48733086305042,         // 0  256 / pi
+    0.01227184630308513,       // 1  pi / 256 (fp64)
+    4.783776559169348e-19,     // 2  pi / 256 - fp64(pi / 256)
+    -1.0 / 6.0, 1.0 / 120.0};  // 3, 4  sin r = r + r^3 (S1 + z S2), |r| <= pi/512: r^7/5040 < 1e-17 r
 #else
-static __device__ const double2 hb_kSinCosTab[HB_SC_N] = {   // {sin, cos}(k*pi/256), correctly rounded
-    {0, 1}, {0.012271538285719925, 0.9999247018391445},
-    {0.024541228522912288, 0.99969881869620425}, {0.036807222941358832, 0.99932238458834954},
-    {0.049067674327418015, 0.99879545620517241}, {0.061320736302208578, 0.99811811290014918},
-    {0.073564563599667426, 0.99729045667869021}, {0.085797312344439894, 0.996312612182778},
-    {0.098017140329560604, 0.99518472667219693}, {0.11022220729388306, 0.99390697000235606},
-    {0.1224106751992162, 0.99247953459870997}, {0.1345807085071262, 0.99090263542778001},
-    {0.14673047445536175, 0.98917650996478101}, {0.15885814333386145, 0.98730141815785843},
-    {0.17096188876030122, 0.98527764238894122}, {0.18303988795514095, 0.98310548743121629},
-    {0.19509032201612828, 0.98078528040323043}, {0.20711137619221856, 0.97831737071962765},
-    {0.2191012401568698, 0.97570213003852857}, {0.23105810828067111, 0.97293995220556018},
-    {0.2429801799032639, 0.97003125319454397}, {0.25486565960451457, 0.96697647104485207},
-    {0.26671275747489837, 0.96377606579543984}, {0.27851968938505312, 0.96043051941556579},
-    {0.29028467725446239, 0.95694033573220882}, {0.30200594931922808, 0.95330604035419386},
-    {0.31368174039889146, 0.94952818059303667}, {0.32531029216226293, 0.94560732538052128},
-    {0.33688985339222005, 0.94154406518302081}, {0.34841868024943456, 0.93733901191257496},
-    {0.35989503653498817, 0.93299279883473885}, {0.37131719395183754, 0.92850608047321559},
-    {0.38268343236508978, 0.92387953251128674}, {0.3939920400610481, 0.91911385169005777},
-    {0.40524131400498986, 0.91420975570353069}, {0.41642956009763721, 0.90916798309052238},
-    {0.42755509343028208, 0.90398929312344334}, {0.43861623853852766, 0.89867446569395382},
-    {0.4496113296546066, 0.89322430119551532}, {0.46053871095824001, 0.88763962040285393},
-    {0.47139673682599764, 0.88192126434835505}, {0.48218377207912277, 0.8760700941954066},
-    {0.49289819222978404, 0.87008699110871146}, {0.50353838372571758, 0.8639728561215867},
-    {0.51410274419322177, 0.85772861000027212}, {0.52458968267846895, 0.8513551931052652},
-    {0.53499761988709726, 0.84485356524970712}, {0.54532498842204646, 0.83822470555483808},
-    {0.55557023301960218, 0.83146961230254524}, {0.56573181078361323, 0.82458930278502529},
-    {0.57580819141784534, 0.81758481315158371}, {0.58579785745643886, 0.81045719825259477},
-    {0.59569930449243336, 0.80320753148064494}, {0.60551104140432555, 0.79583690460888357},
-    {0.61523159058062682, 0.78834642762660623}, {0.62485948814238634, 0.78073722857209449},
-    {0.63439328416364549, 0.77301045336273699}, {0.6438315428897915, 0.76516726562245896},
-    {0.65317284295377676, 0.75720884650648457}, {0.66241577759017178, 0.74913639452345937},
-    {0.67155895484701844, 0.74095112535495911}, {0.68060099779545302, 0.73265427167241282},
-    {0.68954054473706694, 0.72424708295146689}, {0.6983762494089728, 0.71573082528381871},
-    {0.70710678118654757, 0.70710678118654757}, {0.71573082528381871, 0.6983762494089728},
-    {0.72424708295146689, 0.68954054473706694}, {0.73265427167241282, 0.68060099779545302},
-    {0.74095112535495911, 0.67155895484701844}, {0.74913639452345937, 0.66241577759017178},
-    {0.75720884650648457, 0.65317284295377676}, {0.76516726562245896, 0.6438315428897915},
-    {0.77301045336273699, 0.63439328416364549}, {0.78073722857209449, 0.62485948814238634},
-    {0.78834642762660623, 0.61523159058062682}, {0.79583690460888357, 0.60551104140432555},
-    {0.80320753148064494, 0.59569930449243336}, {0.81045719825259477, 0.58579785745643886},
-    {0.81758481315158371, 0.57580819141784534}, {0.82458930278502529, 0.56573181078361323},
-    {0.83146961230254524, 0.55557023301960218}, {0.83822470555483808, 0.54532498842204646},
-    {0.84485356524970712, 0.53499761988709726}, {0.8513551931052652, 0.52458968267846895},
-    {0.85772861000027212, 0.51410274419322177}, {0.8639728561215867, 0.50353838372571758},
-    {0.87008699110871146, 0.49289819222978404}, {0.8760700941954066, 0.48218377207912277},
-    {0.88192126434835505, 0.47139673682599764}, {0.88763962040285393, 0.46053871095824001},
-    {0.89322430119551532, 0.4496113296546066}, {0.89867446569395382, 0.43861623853852766},
-    {0.90398929312344334, 0.42755509343028208}, {0.90916798309052238, 0.41642956009763721},
-    {0.91420975570353069, 0.40524131400498986}, {0.91911385169005777, 0.3939920400610481},
-    {0.92387953251128674, 0.38268343236508978}, {0.92850608047321559, 0.37131719395183754},
-    {0.93299279883473885, 0.35989503653498817}, {0.93733901191257496, 0.34841868024943456},
-    {0.94154406518302081, 0.33688985339222005}, {0.94560732538052128, 0.32531029216226293},
-    {0.94952818059303667, 0.31368174039889146}, {0.95330604035419386, 0.30200594931922808},
-    {0.95694033573220882, 0.29028467725446239}, {0.96043051941556579, 0.27851968938505312},
-    {0.96377606579543984, 0.26671275747489837}, {0.96697647104485207, 0.25486565960451457},
-    {0.97003125319454397, 0.2429801799032639}, {0.97293995220556018, 0.23105810828067111},
-    {0.97570213003852857, 0.2191012401568698}, {0.97831737071962765, 0.20711137619221856},
-    {0.98078528040323043, 0.19509032201612828}, {0.98310548743121629, 0.18303988795514095},
-    {0.98527764238894122, 0.17096188876030122}, {0.98730141815785843, 0.15885814333386145},
-    {0.98917650996478101, 0.14673047445536175}, {0.99090263542778001, 0.1345807085071262},
-    {0.99247953459870997, 0.1224106751992162}, {0.99390697000235606, 0.11022220729388306},
-    {0.99518472667219693, 0.098017140329560604}, {0.996312612182778, 0.085797312344439894},
-    {0.99729045667869021, 0.073564563599667426}, {0.99811811290014918, 0.061320736302208578},
-    {0.99879545620517241, 0.049067674327418015}, {0.99932238458834954, 0.036807222941358832},
-    {0.99969881869620425, 0.024541228522912288}, {0.9999247018391445, 0.012271538285719925},
-    {1, 0}, {0.9999247018391445, -0.012271538285719925},
-    {0.99969881869620425, -0.024541228522912288}, {0.99932238458834954, -0.036807222941358832},
-    {0.99879545620517241, -0.049067674327418015}, {0.99811811290014918, -0.061320736302208578},
-    {0.99729045667869021, -0.073564563599667426}, {0.996312612182778, -0.085797312344439894},
-    {0.99518472667219693, -0.098017140329560604}, {0.99390697000235606, -0.11022220729388306},
-    {0.99247953459870997, -0.1224106751992162}, {0.99090263542778001, -0.1345807085071262},
-    {0.98917650996478101, -0.14673047445536175}, {0.98730141815785843, -0.15885814333386145},
-    {0.98527764238894122, -0.17096188876030122}, {0.98310548743121629, -0.18303988795514095},
-    {0.98078528040323043, -0.19509032201612828}, {0.97831737071962765, -0.20711137619221856},
-    {0.97570213003852857, -0.2191012401568698}, {0.97293995220556018, -0.23105810828067111},
-    {0.97003125319454397, -0.2429801799032639}, {0.96697647104485207, -0.25486565960451457},
-    {0.96377606579543984, -0.26671275747489837}, {0.96043051941556579, -0.27851968938505312},
-    {0.95694033573220882, -0.29028467725446239}, {0.95330604035419386, -0.30200594931922808},
-    {0.94952818059303667, -0.31368174039889146}, {0.94560732538052128, -0.32531029216226293},
-    {0.94154406518302081, -0.33688985339222005}, {0.93733901191257496, -0.34841868024943456},
-    {0.93299279883473885, -0.35989503653498817}, {0.92850608047321559, -0.37131719395183754},
-    {0.92387953251128674, -0.38268343236508978}, {0.91911385169005777, -0.3939920400610481},
-    {0.91420975570353069, -0.40524131400498986}, {0.90916798309052238, -0.41642956009763721},
-    {0.90398929312344334, -0.42755509343028208}, {0.89867446569395382, -0.43861623853852766},
-    {0.89322430119551532, -0.4496113296546066}, {0.88763962040285393, -0.46053871095824001},
-    {0.88192126434835505, -0.47139673682599764}, {0.8760700941954066, -0.48218377207912277},
-    {0.87008699110871146, -0.49289819222978404}, {0.8639728561215867, -0.50353838372571758},
-    {0.85772861000027212, -0.51410274419322177}, {0.8513551931052652, -0.52458968267846895},
-    {0.84485356524970712, -0.53499761988709726}, {0.83822470555483808, -0.54532498842204646},
-    {0.83146961230254524, -0.55557023301960218}, {0.82458930278502529, -0.56573181078361323},
-    {0.81758481315158371, -0.57580819141784534}, {0.81045719825259477, -0.58579785745643886},
-    {0.80320753148064494, -0.59569930449243336}, {0.79583690460888357, -0.60551104140432555},
-    {0.78834642762660623, -0.61523159058062682}, {0.78073722857209449, -0.62485948814238634},
-    {0.77301045336273699, -0.63439328416364549}, {0.76516726562245896, -0.6438315428897915},
-    {0.75720884650648457, -0.65317284295377676}, {0.74913639452345937, -0.66241577759017178},
-    {0.74095112535495911, -0.67155895484701844}, {0.73265427167241282, -0.68060099779545302},
-    {0.72424708295146689, -0.68954054473706694}, {0.71573082528381871, -0.6983762494089728},
-    {0.70710678118654757, -0.70710678118654757}, {0.6983762494089728, -0.71573082528381871},
-    {0.68954054473706694, -0.72424708295146689}, {0.68060099779545302, -0.73265427167241282},
-    {0.67155895484701844, -0.74095112535495911}, {0.66241577759017178, -0.74913639452345937},
-    {0.65317284295377676, -0.75720884650648457}, {0.6438315428897915, -0.76516726562245896},
-    {0.63439328416364549, -0.77301045336273699}, {0.62485948814238634, -0.78073722857209449},
-    {0.61523159058062682, -0.78834642762660623}, {0.60551104140432555, -0.79583690460888357},
-    {0.59569930449243336, -0.80320753148064494}, {0.58579785745643886, -0.81045719825259477},
-    {0.57580819141784534, -0.81758481315158371}, {0.56573181078361323, -0.82458930278502529},
-    {0.55557023301960218, -0.83146961230254524}, {0.54532498842204646, -0.83822470555483808},
-    {0.53499761988709726, -0.84485356524970712}, {0.52458968267846895, -0.8513551931052652},
-    {0.51410274419322177, -0.85772861000027212}, {0.50353838372571758, -0.8639728561215867},
-    {0.49289819222978404, -0.87008699110871146}, {0.48218377207912277, -0.8760700941954066},
-    {0.47139673682599764, -0.88192126434835505}, {0.46053871095824001, -0.88763962040285393},
-    {0.4496113296546066, -0.89322430119551532}, {0.43861623853852766, -0.89867446569395382},
-    {0.42755509343028208, -0.90398929312344334}, {0.41642956009763721, -0.90916798309052238},
-    {0.40524131400498986, -0.91420975570353069}, {0.3939920400610481, -0.91911385169005777},
-    {0.38268343236508978, -0.92387953251128674}, {0.37131719395183754, -0.92850608047321559},
-    {0.35989503653498817, -0.93299279883473885}, {0.34841868024943456, -0.93733901191257496},
-    {0.33688985339222005, -0.94154406518302081}, {0.32531029216226293, -0.94560732538052128},
-    {0.31368174039889146, -0.94952818059303667}, {0.30200594931922808, -0.95330604035419386},
-    {0.29028467725446239, -0.95694033573220882}, {0.27851968938505312, -0.96043051941556579},
-    {0.26671275747489837, -0.96377606579543984}, {0.25486565960451457, -0.96697647104485207},
-    {0.2429801799032639, -0.97003125319454397}, {0.23105810828067111, -0.97293995220556018},
-    {0.2191012401568698, -0.97570213003852857}, {0.20711137619221856, -0.97831737071962765},
-    {0.19509032201612828, -0.98078528040323043}, {0.18303988795514095, -0.98310548743121629},
-    {0.17096188876030122, -0.98527764238894122}, {0.15885814333386145, -0.98730141815785843},
-    {0.14673047445536175, -0.98917650996478101}, {0.1345807085071262, -0.99090263542778001},
-    {0.1224106751992162, -0.99247953459870997}, {0.11022220729388306, -0.99390697000235606},
-    {0.098017140329560604, -0.99518472667219693}, {0.085797312344439894, -0.996312612182778},
-    {0.073564563599667426, -0.99729045667869021}, {0.061320736302208578, -0.99811811290014918},
-    {0.049067674327418015, -0.99879545620517241}, {0.036807222941358832, -0.99932238458834954},
-    {0.024541228522912288, -0.99969881869620425}, {0.012271538285719925, -0.9999247018391445},
-    {0, -1}, {-0.012271538285719925, -0.9999247018391445},
-    {-0.024541228522912288, -0.99969881869620425}, {-0.036807222941358832, -0.99932238458834954},
-    {-0.049067674327418015, -0.99879545620517241}, {-0.061320736302208578, -0.99811811290014918},
-    {-0.073564563599667426, -0.99729045667869021}, {-0.085797312344439894, -0.996312612182778},
-    {-0.098017140329560604, -0.99518472667219693}, {-0.11022220729388306, -0.99390697000235606},
-    {-0.1224106751992162, -0.99247953459870997}, {-0.1345807085071262, -0.99090263542778001},
-    {-0.14673047445536175, -0.98917650996478101}, {-0.15885814333386145, -0.98730141815785843},
-    {-0.17096188876030122, -0.98527764238894122}, {-0.18303988795514095, -0.98310548743121629},
-    {-0.19509032201612828, -0.98078528040323043}, {-0.20711137619221856, -0.97831737071962765},
-    {-0.2191012401568698, -0.97570213003852857}, {-0.23105810828067111, -0.97293995220556018},
-    {-0.2429801799032639, -0.97003125319454397}, {-0.25486565960451457, -0.96697647104485207},
-    {-0.26671275747489837, -0.96377606579543984}, {-0.27851968938505312, -0.96043051941556579},
-    {-0.29028467725446239, -0.95694033573220882}, {-0.30200594931922808, -0.95330604035419386},
-    {-0.31368174039889146, -0.94952818059303667}, {-0.32531029216226293, -0.94560732538052128},
-    {-0.33688985339222005, -0.94154406518302081}, {-0.34841868024943456, -0.93733901191257496},
-    {-0.35989503653498817, -0.93299279883473885}, {-0.37131719395183754, -0.92850608047321559},
-    {-0.38268343236508978, -0.92387953251128674}, {-0.3939920400610481, -0.91911385169005777},
-    {-0.40524131400498986, -0.91420975570353069}, {-0.41642956009763721, -0.90916798309052238},
-    {-0.42755509343028208, -0.90398929312344334}, {-0.43861623853852766, -0.89867446569395382},
-    {-0.4496113296546066, -0.89322430119551532}, {-0.46053871095824001, -0.88763962040285393},
-    {-0.47139673682599764, -0.88192126434835505}, {-0.48218377207912277, -0.8760700941954066},
-    {-0.49289819222978404, -0.87008699110871146}, {-0.50353838372571758, -0.8639728561215867},
-    {-0.51410274419322177, -0.85772861000027212}, {-0.52458968267846895, -0.8513551931052652},
-    {-0.53499761988709726, -0.84485356524970712}, {-0.54532498842204646, -0.83822470555483808},
-    {-0.55557023301960218, -0.83146961230254524}, {-0.56573181078361323, -0.82458930278502529},
-    {-0.57580819141784534, -0.81758481315158371}, {-0.58579785745643886, -0.81045719825259477},
-    {-0.59569930449243336, -0.80320753148064494}, {-0.60551104140432555, -0.79583690460888357},
-    {-0.61523159058062682, -0.78834642762660623}, {-0.62485948814238634, -0.78073722857209449},
-    {-0.63439328416364549, -0.77301045336273699}, {-0.6438315428897915, -0.76516726562245896},
-    {-0.65317284295377676, -0.75720884650648457}, {-0.66241577759017178, -0.74913639452345937},
-    {-0.67155895484701844, -0.74095112535495911}, {-0.68060099779545302, -0.73265427167241282},
-    {-0.68954054473706694, -0.72424708295146689}, {-0.6983762494089728, -0.71573082528381871},
-    {-0.70710678118654757, -0.70710678118654757}, {-0.71573082528381871, -0.6983762494089728},
-    {-0.72424708295146689, -0.68954054473706694}, {-0.73265427167241282, -0.68060099779545302},
-    {-0.74095112535495911, -0.67155895484701844}, {-0.74913639452345937, -0.66241577759017178},
-    {-0.75720884650648457, -0.65317284295377676}, {-0.76516726562245896, -0.6438315428897915},
-    {-0.77301045336273699, -0.63439328416364549}, {-0.78073722857209449, -0.62485948814238634},
-    {-0.78834642762660623, -0.61523159058062682}, {-0.79583690460888357, -0.60551104140432555},
-    {-0.80320753148064494, -0.59569930449243336}, {-0.81045719825259477, -0.58579785745643886},
-    {-0.81758481315158371, -0.57580819141784534}, {-0.82458930278502529, -0.56573181078361323},
-    {-0.83146961230254524, -0.55557023301960218}, {-0.83822470555483808, -0.54532498842204646},
-    {-0.84485356524970712, -0.53499761988709726}, {-0.8513551931052652, -0.52458968267846895},
-    {-0.85772861000027212, -0.51410274419322177}, {-0.8639728561215867, -0.50353838372571758},
-    {-0.87008699110871146, -0.49289819222978404}, {-0.8760700941954066, -0.48218377207912277},
-    {-0.88192126434835505, -0.47139673682599764}, {-0.88763962040285393, -0.46053871095824001},
-    {-0.89322430119551532, -0.4496113296546066}, {-0.89867446569395382, -0.43861623853852766},
-    {-0.90398929312344334, -0.42755509343028208}, {-0.90916798309052238, -0.41642956009763721},
-    {-0.91420975570353069, -0.40524131400498986}, {-0.91911385169005777, -0.3939920400610481},
-    {-0.92387953251128674, -0.38268343236508978}, {-0.92850608047321559, -0.37131719395183754},
-    {-0.93299279883473885, -0.35989503653498817}, {-0.93733901191257496, -0.34841868024943456},
-    {-0.94154406518302081, -0.33688985339222005}, {-0.94560732538052128, -0.32531029216226293},
-    {-0.94952818059303667, -0.31368174039889146}, {-0.95330604035419386, -0.30200594931922808},
-    {-0.95694033573220882, -0.29028467725446239}, {-0.96043051941556579, -0.27851968938505312},
-    {-0.96377606579543984, -0.26671275747489837}, {-0.96697647104485207, -0.25486565960451457},
-    {-0.97003125319454397, -0.2429801799032639}, {-0.97293995220556018, -0.23105810828067111},
-    {-0.97570213003852857, -0.2191012401568698}, {-0.97831737071962765, -0.20711137619221856},
-    {-0.98078528040323043, -0.19509032201612828}, {-0.98310548743121629, -0.18303988795514095},
-    {-0.98527764238894122, -0.17096188876030122}, {-0.98730141815785843, -0.15885814333386145},
-    {-0.98917650996478101, -0.14673047445536175}, {-0.99090263542778001, -0.1345807085071262},
-    {-0.99247953459870997, -0.1224106751992162}, {-0.99390697000235606, -0.11022220729388306},
-    {-0.99518472667219693, -0.098017140329560604}, {-0.996312612182778, -0.085797312344439894},
-    {-0.99729045667869021, -0.073564563599667426}, {-0.99811811290014918, -0.061320736302208578},
-    {-0.99879545620517241, -0.049067674327418015}, {-0.99932238458834954, -0.036807222941358832},
-    {-0.99969881869620425, -0.024541228522912288}, {-0.9999247018391445, -0.012271538285719925},
-    {-1, 0}, {-0.9999247018391445, 0.012271538285719925},
-    {-0.99969881869620425, 0.024541228522912288}, {-0.99932238458834954, 0.036807222941358832},
-    {-0.99879545620517241, 0.049067674327418015}, {-0.99811811290014918, 0.061320736302208578},
-    {-0.99729045667869021, 0.073564563599667426}, {-0.996312612182778, 0.085797312344439894},
-    {-0.99518472667219693, 0.098017140329560604}, {-0.99390697000235606, 0.11022220729388306},
-    {-0.99247953459870997, 0.1224106751992162}, {-0.99090263542778001, 0.1345807085071262},
-    {-0.98917650996478101, 0.14673047445536175}, {-0.98730141815785843, 0.15885814333386145},
-    {-0.98527764238894122, 0.17096188876030122}, {-0.98310548743121629, 0.18303988795514095},
-    {-0.98078528040323043, 0.19509032201612828}, {-0.97831737071962765, 0.20711137619221856},
-    {-0.97570213003852857, 0.2191012401568698}, {-0.97293995220556018, 0.23105810828067111},
-    {-0.97003125319454397, 0.2429801799032639}, {-0.96697647104485207, 0.25486565960451457},
-    {-0.96377606579543984, 0.26671275747489837}, {-0.96043051941556579, 0.27851968938505312},
-    {-0.95694033573220882, 0.29028467725446239}, {-0.95330604035419386, 0.30200594931922808},
-    {-0.94952818059303667, 0.31368174039889146}, {-0.94560732538052128, 0.32531029216226293},
-    {-0.94154406518302081, 0.33688985339222005}, {-0.93733901191257496, 0.34841868024943456},
-    {-0.93299279883473885, 0.35989503653498817}, {-0.92850608047321559, 0.37131719395183754},
-    {-0.92387953251128674, 0.38268343236508978}, {-0.91911385169005777, 0.3939920400610481},
-    {-0.91420975570353069, 0.40524131400498986}, {-0.90916798309052238, 0.41642956009763721},
-    {-0.90398929312344334, 0.42755509343028208}, {-0.89867446569395382, 0.43861623853852766},
-    {-0.89322430119551532, 0.4496113296546066}, {-0.88763962040285393, 0.46053871095824001},
-    {-0.88192126434835505, 0.47139673682599764}, {-0.8760700941954066, 0.48218377207912277},
-    {-0.87008699110871146, 0.49289819222978404}, {-0.8639728561215867, 0.50353838372571758},
-    {-0.85772861000027212, 0.51410274419322177}, {-0.8513551931052652, 0.52458968267846895},
-    {-0.84485356524970712, 0.53499761988709726}, {-0.83822470555483808, 0.54532498842204646},
-    {-0.83146961230254524, 0.55557023301960218}, {-0.82458930278502529, 0.56573181078361323},
-    {-0.81758481315158371, 0.57580819141784534}, {-0.81045719825259477, 0.58579785745643886},
-    {-0.80320753148064494, 0.59569930449243336}, {-0.79583690460888357, 0.60551104140432555},
-    {-0.78834642762660623, 0.61523159058062682}, {-0.78073722857209449, 0.62485948814238634},
-    {-0.77301045336273699, 0.63439328416364549}, {-0.76516726562245896, 0.6438315428897915},
-    {-0.75720884650648457, 0.65317284295377676}, {-0.74913639452345937, 0.66241577759017178},
-    {-0.74095112535495911, 0.67155895484701844}, {-0.73265427167241282, 0.68060099779545302},
-    {-0.72424708295146689, 0.68954054473706694}, {-0.71573082528381871, 0.6983762494089728},
-    {-0.70710678118654757, 0.70710678118654757}, {-0.6983762494089728, 0.71573082528381871},
-    {-0.68954054473706694, 0.72424708295146689}, {-0.68060099779545302, 0.73265427167241282},
-    {-0.67155895484701844, 0.74095112535495911}, {-0.66241577759017178, 0.74913639452345937},
-    {-0.65317284295377676, 0.75720884650648457}, {-0.6438315428897915, 0.76516726562245896},
-    {-0.63439328416364549, 0.77301045336273699}, {-0.62485948814238634, 0.78073722857209449},
-    {-0.61523159058062682, 0.78834642762660623}, {-0.60551104140432555, 0.79583690460888357},
-    {-0.59569930449243336, 0.80320753148064494}, {-0.58579785745643886, 0.81045719825259477},
-    {-0.57580819141784534, 0.81758481315158371}, {-0.56573181078361323, 0.82458930278502529},
-    {-0.55557023301960218, 0.83146961230254524}, {-0.54532498842204646, 0.83822470555483808},
-    {-0.53499761988709726, 0.84485356524970712}, {-0.52458968267846895, 0.8513551931052652},
-    {-0.51410274419322177, 0.85772861000027212}, {-0.50353838372571758, 0.8639728561215867},
-    {-0.49289819222978404, 0.87008699110871146}, {-0.48218377207912277, 0.8760700941954066},
-    {-0.47139673682599764, 0.88192126434835505}, {-0.46053871095824001, 0.88763962040285393},
-    {-0.4496113296546066, 0.89322430119551532}, {-0.43861623853852766, 0.89867446569395382},
-    {-0.42755509343028208, 0.90398929312344334}, {-0.41642956009763721, 0.90916798309052238},
-    {-0.40524131400498986, 0.91420975570353069}, {-0.3939920400610481, 0.91911385169005777},
-    {-0.38268343236508978, 0.92387953251128674}, {-0.37131719395183754, 0.92850608047321559},
-    {-0.35989503653498817, 0.93299279883473885}, {-0.34841868024943456, 0.93733901191257496},
-    {-0.33688985339222005, 0.94154406518302081}, {-0.32531029216226293, 0.94560732538052128},
-    {-0.31368174039889146, 0.94952818059303667}, {-0.30200594931922808, 0.95330604035419386},
-    {-0.29028467725446239, 0.95694033573220882}, {-0.27851968938505312, 0.96043051941556579},
-    {-0.26671275747489837, 0.96377606579543984}, {-0.25486565960451457, 0.96697647104485207},
-    {-0.2429801799032639, 0.97003125319454397}, {-0.23105810828067111, 0.97293995220556018},
-    {-0.2191012401568698, 0.97570213003852857}, {-0.20711137619221856, 0.97831737071962765},
-    {-0.19509032201612828, 0.98078528040323043}, {-0.18303988795514095, 0.98310548743121629},
-    {-0.17096188876030122, 0.98527764238894122}, {-0.15885814333386145, 0.98730141815785843},
-    {-0.14673047445536175, 0.98917650996478101}, {-0.1345807085071262, 0.99090263542778001},
-    {-0.1224106751992162, 0.99247953459870997}, {-0.11022220729388306, 0.99390697000235606},
-    {-0.098017140329560604, 0.99518472667219693}, {-0.085797312344439894, 0.996312612182778},
-    {-0.073564563599667426, 0.99729045667869021}, {-0.061320736302208578, 0.99811811290014918},
-    {-0.049067674327418015, 0.99879545620517241}, {-0.036807222941358832, 0.99932238458834954},
-    {-0.024541228522912288, 0.99969881869620425}, {-0.012271538285719925, 0.9999247018391445},
-};
-static __device__ __constant__ double hb_kSC[10] = {
-    81.48733086305042,           // 0  256/pi
-    6755399441055744.0,           // 1  1.5 * 2^52
-    0.01227184630308513,         // 2  pi/256 hi
-    4.783776559169348e-19,       // 3  pi/256 lo
-    -1.0 / 6.0, 1.0 / 120.0, 0.0,                // 4..5   sin r = r + r^3 (S1 + z S2),     |r| <= pi/512: r^7/5040 < 1e-17 r
-    -0.5, 1.0 / 24.0, 0.0};                      // 7..8   cos r - 1 = z (C1 + z C2),       z^3/720 < 8e-17
+#error "HB_SC_LOG2 must be 9 or 11"
 #endif
 
-HB_DEV void hb_tab_init(double2* tab) {
-  if (blockDim.x == HB_BLOCK) {   // the size every kernel is launched with: HB_SC_N / HB_BLOCK loads per thread, fully unrolled
-#pragma unroll
-    for (int j = 0; j < HB_SC_N / HB_BLOCK; j++) {
-      const int t = threadIdx.x + j * HB_BLOCK;
-      const double2 v = hb_kSinCosTab[t];
-#pragma unroll
-      for (int r = 0; r < HB_SC_REP; r++) tab[t * HB_SC_REP + r] = v;
-    }
-  } else {                        // (HB_BLOCK experiments) plain loop: no trip-count division in front of it
-#pragma unroll 1
-    for (int t = threadIdx.x; t < HB_SC_N; t += blockDim.x) {
-      const double2 v = hb_kSinCosTab[t];
-#pragma unroll
-      for (int r = 0; r < HB_SC_REP; r++) tab[t * HB_SC_REP + r] = v;
-    }
+// Shared-memory image of the table + the mbarrier its bulk copy completes on.
+struct HbTab {
+  double2 e[HB_SC_N];
+  unsigned long long bar;
+};
+#ifndef HB_TAB_BULK
+#define HB_TAB_BULK (HB_SC_LOG2 == HB_SC_TAB_LOG2)   // whole table: ONE cp.async.bulk (TMA, UBLKCP) per CTA instead of a load/store loop
+#endif
+// Stage the table.  Reads only constant data, so it runs BEFORE griddepcontrol.wait, under the previous kernel's tail.
+HB_DEV void hb_tab_issue(HbTab* tab) {
+#ifndef HB_HOST_EMU
+#if HB_TAB_BULK
+  if (threadIdx.x == 0) {
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&tab->bar), dst = (unsigned)__cvta_generic_to_shared(tab->e);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((unsigned)sizeof(tab->e)) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(hb_kSinCosTab), "r"((unsigned)sizeof(tab->e)), "r"(bar) : "memory");
   }
-  __syncthreads();
+#else
+#pragma unroll 1
+  for (int t = threadIdx.x; t < HB_SC_N; t += blockDim.x) tab->e[t] = hb_kSinCosTab[t << (HB_SC_TAB_LOG2 - HB_SC_LOG2)];
+#endif
+  __syncthreads();   // the initialised mbarrier (or the staged entries) are visible to every thread of the CTA
+#else
+  (void)tab;
+#endif
+}
+HB_DEV void hb_tab_wait(HbTab* tab) {
+#if !defined(HB_HOST_EMU) && HB_TAB_BULK
+  const unsigned bar = (unsigned)__cvta_generic_to_shared(&tab->bar);
+  unsigned done;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar) : "memory");
+  } while (!done);
+#else
+  (void)tab;
+#endif
 }
 
 template <bool FAST>
@@ -577,46 +299,29 @@ HB_DEV void hb_sincos(HbCtx& cx, double x, double* sp, double* cp) {
   if constexpr (!FAST) {
     sincos(x, sp, cp);
   } else {
-    cx.oob |= (unsigned)((__double2hiint(x) & 0x7fffffff) >= 0x40F86A00);   // |x| >= 1e5, inf or nan (integer pipe)
-    // 1.5 * 2^52 has a zero low word: written as a literal it becomes the 32-bit immediate operand of DFMA / DADD instead
-    // of a register pair (8 fewer three-register DFMAs per RK4 step, +0.7 %: profiles/r1ac/ab_sc_literals.txt)
-    const double t = fma(x, hb_kSC[0], 6755399441055744.0);
+    const double t = fma(x, hb_kSC[0], HB_SC_MAGIC);
+    cx.oob |= (unsigned)__double2hiint(t) ^ 0x43380000u;   // 0 <=> -2^31 <= k < 2^31 (inf/nan/huge arguments land elsewhere)
     double2 sc;   // one LDS.128 with a 32-bit shared address (no generic->shared conversion in the loop)
 #ifdef HB_HOST_EMU
-    sc = hb_kSinCosTab[__double2loint(t) & (HB_SC_N - 1)];
+    sc = hb_kSinCosTab[(__double2loint(t) & (HB_SC_N - 1)) << (HB_SC_TAB_LOG2 - HB_SC_LOG2)];
 #else
-    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(sc.x), "=d"(sc.y) : "r"(cx.tab_s + ((__double2loint(t) & (HB_SC_N - 1)) << (4 + HB_SC_REP_LOG2))));
+    unsigned addr;
+    asm("{\n\t.reg .u32 k;\n\tand.b32 k, %1, %2;\n\tmad.lo.u32 %0, k, 16, %3;\n\t}" : "=r"(addr) : "r"(__double2loint(t)), "n"(HB_SC_N - 1), "r"(cx.tab_s));
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(sc.x), "=d"(sc.y) : "r"(addr));
 #endif
-    const double kf = t - 6755399441055744.0;
-#ifdef HB_SC_LITERALS    // experiment: every constant of the 512-entry variant as a literal (ptxas picks the operand form)
-    double r = fma(-kf, 0.01227184630308513, x);
-    r = fma(-kf, 4.783776559169348e-19, r);
-#else
-    double r = fma(-kf, hb_kSC[2], x);
-    r = fma(-kf, hb_kSC[3], r);
+    const double kf = t - HB_SC_MAGIC;
+    double r = fma(-kf, hb_kSC[1], x);
+#if HB_SC_CW2
+    r = fma(-kf, hb_kSC[2], r);
 #endif
     const double z = r * r;
-#if HB_SC_LOG2 == 7
-    double ps = fma(z, hb_kSC[6], hb_kSC[5]);
-    double pc = fma(z, hb_kSC[9], hb_kSC[8]);
-    ps = fma(z, ps, hb_kSC[4]);
-    pc = fma(z, pc, hb_kSC[7]);
-#elif defined(HB_SC_LITERALS)
-    const double ps = fma(z, 1.0 / 120.0, -1.0 / 6.0);
-    const double pc = fma(z, 1.0 / 24.0, -0.5);
+#if HB_SC_LOG2 == 11
+    const double sr = fma(z * r, hb_kSC[3], r);                           // sin r
+    const double cm = z * fma(z, 1.0 / 24.0, -0.5);                       // cos r - 1
 #else
-    const double ps = fma(z, hb_kSC[5], hb_kSC[4]);
-    const double pc = fma(z, hb_kSC[8], hb_kSC[7]);
+    const double sr = fma(z * r, fma(z, hb_kSC[4], hb_kSC[3]), r);
+    const double cm = z * fma(z, 1.0 / 24.0, -0.5);                       // z^3/720 < 8e-17
 #endif
-    // sin r = r + (z r) ps.  The 2-register-operand form fma(r, z * ps, r) saves a 3-operand DFMA (3 issue clocks instead
-    // of 2, profiles/r1l/fp64_operands.txt) but costs 4 registers and with them a resident CTA: measured 2 % slower at one
-    // step per launch (profiles/r1p/ab_launch_bounds.txt), so it stays an experiment switch.
-#ifdef HB_SR_2OP
-    const double sr = fma(r, z * ps, r);
-#else
-    const double sr = fma(z * r, ps, r);
-#endif
-    const double cm = z * pc;                 // cos r - 1
     *sp = fma(sc.y, sr, fma(sc.x, cm, sc.x));    // sin(a + r) = sin a + (sin a (cos r - 1) + cos a sin r)
     *cp = fma(-sc.x, sr, fma(sc.y, cm, sc.y));   // cos(a + r) = cos a + (cos a (cos r - 1) - sin a sin r)
   }
@@ -692,6 +397,9 @@ HB_DEV void hb_mass(const double* wJ, const double* Jv, double* A) {
 // pivot test on the integer pipe: true unless d is a positive normal number (NaN passes here and is
 // caught by the non-finite check on the result)
 HB_DEV bool hb_bad_pivot(double d) { return __double2hiint(d) < 0x00100000; }
+// The test is deferred: the solves only keep the smallest pivot high word seen (ONE integer min per pivot instead of a
+// compare + select into the flag word); hb_ctx_flags applies hb_bad_pivot to it once per trajectory.
+HB_DEV void hb_piv(int& minpiv, double d) { const int h = __double2hiint(d); minpiv = h < minpiv ? h : minpiv; }
 
 struct HbRegVec {   // right-hand side held in registers
   const double* b;
@@ -703,17 +411,18 @@ struct HbSmemVec {  // right-hand side parked in shared memory (element j at b[j
   HB_DEV double operator()(int j) const { return hb_lds(b + j * STRIDE); }
 };
 template <int N, class BV>
-HB_DEV void hb_spd_solve_v(double* A, const BV b, double* x, int& flag);
+HB_DEV void hb_spd_solve_v(double* A, const BV b, double* x, int& minpiv);
 template <int N>
-HB_DEV void hb_spd_solve(double* A, const double* b, double* x, int& flag) { hb_spd_solve_v<N>(A, HbRegVec{b}, x, flag); }
+HB_DEV void hb_spd_solve(double* A, const double* b, double* x, int& minpiv) { hb_spd_solve_v<N>(A, HbRegVec{b}, x, minpiv); }
 template <int N, class BV>
-HB_DEV void hb_spd_solve_v(double* A, const BV b, double* x, int& flag) {
+HB_DEV void hb_spd_solve_v(double* A, const BV b, double* x, int& minpiv) {
   if constexpr (N == 1) {
-    if (hb_bad_pivot(A[0])) flag |= HB_FLAG_NOT_SPD;
+    hb_piv(minpiv, A[0]);
     x[0] = b(0) * hb_rcp(A[0]);
   } else if constexpr (N == 2) {
     const double det = fma(A[0], A[2], -A[1] * A[1]);
-    if (hb_bad_pivot(A[0]) || hb_bad_pivot(det)) flag |= HB_FLAG_NOT_SPD;
+    hb_piv(minpiv, A[0]);
+    hb_piv(minpiv, det);
     const double id = hb_rcp(det);
     const double n0 = fma(A[2], b(0), -A[1] * b(1));
     const double n1 = fma(A[0], b(1), -A[1] * b(0));
@@ -728,7 +437,9 @@ HB_DEV void hb_spd_solve_v(double* A, const BV b, double* x, int& flag) {
     const double c00 = fma(m11, m22, -m21 * m21), c01 = fma(m20, m21, -m10 * m22), c02 = fma(m10, m21, -m20 * m11);
     const double c11 = fma(m00, m22, -m20 * m20), c12 = fma(m10, m20, -m00 * m21), c22 = fma(m00, m11, -m10 * m10);
     const double det = fma(m00, c00, fma(m10, c01, m20 * c02));
-    if (hb_bad_pivot(m00) || hb_bad_pivot(c22) || hb_bad_pivot(det)) flag |= HB_FLAG_NOT_SPD;
+    hb_piv(minpiv, m00);
+    hb_piv(minpiv, c22);
+    hb_piv(minpiv, det);
     const double id = hb_rcp(det);
     const double b0 = b(0), b1 = b(1), b2 = b(2);
     x[0] = fma(c00, b0, fma(c01, b1, c02 * b2)) * id;
@@ -747,7 +458,7 @@ HB_DEV void hb_spd_solve_v(double* A, const BV b, double* x, int& flag) {
         v[k] = A[hb_tri(j, k)] * A[hb_tri(k, k)];   // L_jk d_k   (A_kk holds d_k)
         d = fma(-A[hb_tri(j, k)], v[k], d);
       });
-      if (hb_bad_pivot(d)) flag |= HB_FLAG_NOT_SPD;
+      hb_piv(minpiv, d);
       A[hb_tri(j, j)] = d;
       const double id = hb_rcp(d);
       invd[j] = id;
@@ -811,7 +522,7 @@ HB_DEV void hb_ham_eqs_sym(HbCtx& cx, const double* prm, const double* qq, const
 #pragma unroll
       for (int e = 0; e < NE; e++) hb_sts(es + e * B, E[e]);
     }
-    hb_spd_solve_v<N>(A, p, dq, flag);
+    hb_spd_solve_v<N>(A, p, dq, cx.minpiv);
     double E[NE];
 #pragma unroll
     for (int e = 0; e < NE; e++) E[e] = hb_lds(es + e * B);
@@ -819,7 +530,7 @@ HB_DEV void hb_ham_eqs_sym(HbCtx& cx, const double* prm, const double* qq, const
   } else {
     double E[NE > 0 ? NE : 1];
     S::template hpre<FAST>(cx, prm, qq, A, E);
-    hb_spd_solve_v<N>(A, p, dq, flag);
+    hb_spd_solve_v<N>(A, p, dq, cx.minpiv);
     S::template hpost<FAST>(cx, prm, qq, E, dq, dp);
   }
 }
@@ -850,7 +561,7 @@ HB_DEV void hb_ham_eqs(HbCtx& cx, const double* prm, const double* w, const doub
   hb_weigh<S>(w, Jv, wJ);
   double A[N * (N + 1) / 2];
   hb_mass<S>(wJ, Jv, A);
-  hb_spd_solve<N>(A, p, dq, flag);
+  hb_spd_solve<N>(A, p, dq, cx.minpiv);
   double a[M];
   hb_j_mul<S>(wJ, dq, a);
 #pragma unroll
@@ -911,14 +622,14 @@ HB_DEV void hb_velocities(HbCtx& cx, const double* prm, const double* w, const d
     (void)w;
     double A[N * (N + 1) / 2];
     if constexpr (WITH_U) S::template smass_pot<FAST>(cx, prm, qq, A, U); else S::template smass<FAST>(cx, prm, qq, A);
-    hb_spd_solve<N>(A, p, v, flag);
+    hb_spd_solve<N>(A, p, v, cx.minpiv);
     return;
   }
   if constexpr (WITH_U) S::template jac_pot<FAST>(cx, prm, qq, Jv, U); else S::template jac<FAST>(cx, prm, qq, Jv);
   hb_weigh<S>(w, Jv, wJ);
   double A[N * (N + 1) / 2];
   hb_mass<S>(wJ, Jv, A);
-  hb_spd_solve<N>(A, p, v, flag);
+  hb_spd_solve<N>(A, p, v, cx.minpiv);
 }
 
 // ------------------------------------------------------------------------ integrators ------
@@ -1123,32 +834,38 @@ HB_DEV void hb_rkf45_to(HbCtx& cx, const double* prm, const double* w, double (&
 }
 
 // ------------------------------------------------------------------ per-trajectory bodies ----
-// LAY: layout known at compile time inside a kernel instance (-1 = read a.layout; 0 = array of Phases, i.e. a.layout is
-// 0 or 2).  The hot step kernel dispatches once per launch into a LAY = 0 instance, so the per-trajectory load/store
-// carries no SOA code at all — ptxas otherwise if-converts the layout branches and the AOS path issues ~26 predicated-off
-// instructions per trajectory (of ~95 issue clocks of bookkeeping per trajectory-launch, profiles/r1s/fixed_cost.txt).
+// LAY: layout known at compile time inside a kernel instance (-1 = read a.layout; 0 = array of Phases in device memory).
+// The hot step kernels dispatch once per launch into a LAY = 0 instance, so the per-trajectory load/store carries no SOA
+// and no warp-transposed-store code at all — ptxas otherwise if-converts the layout branches and the AOS path issues ~26
+// predicated-off instructions per trajectory.  NST: 1 = exactly one step per launch, compiled as straight-line code (the
+// loop over a.nsteps makes the state a loop-carried value and ptxas copies the prefetched Phase into it: 8-16 moves per
+// trajectory); 0 = a.nsteps steps.
 #ifndef HB_LAYSPEC
 #define HB_LAYSPEC 1
 #endif
-#ifndef HB_UNROLL2
-#define HB_UNROLL2 0       // experiment (round 2 A/B): ping-pong Phase buffers in the grid-stride loop instead of a register copy
+#ifndef HB_PINGPONG
+#define HB_PINGPONG 1      // small records: two Phase buffers swap roles in a 2x unrolled loop (no register copy of the prefetched Phase)
 #endif
-template <int LAY> HB_DEV int hb_lay_of(const HbKArgs& a) { if constexpr (LAY < 0) return a.layout; else return a.layout == 2 ? 2 : 0; }
-// Each hb_traj_* processes trajectory i completely (load -> compute -> store).  FAST=true is inlined
+template <int LAY> HB_DEV int hb_lay_of(const HbKArgs& a) { if constexpr (LAY < 0) return a.layout; else return LAY; }
+// HB_FLAG_* bits of one trajectory: what the integrators raised + the deferred pivot test
+HB_DEV int hb_ctx_flags(const HbCtx& cx, int flag) { return cx.minpiv < 0x00100000 ? (flag | HB_FLAG_NOT_SPD) : flag; }
+// Each hb_traj_* processes trajectory i completely (compute -> store; the kernel body loads).  FAST=true is inlined
 // into the kernel; if any fast primitive left its domain (cx.oob) nothing is stored and the kernel
 // re-runs that one trajectory through the out-of-line FAST=false instance (HB_KERNEL_BODY below).
-template <int D>
-HB_DEV void hb_finish(const HbKArgs& a, long long i, const double (&y)[D], int flag) {
+template <int D, class I>
+HB_DEV void hb_finish(const HbKArgs& a, I i, const double (&y)[D], const HbCtx& cx, int flag) {
+  if (a.flags == nullptr) return;   // (uniform) nobody asked: no finite checks, no flag word
+  flag = hb_ctx_flags(cx, flag);
   bool ok = true;
 #pragma unroll
   for (int c = 0; c < D; c++) ok = ok && hb_finite(y[c]);
   if (!ok) flag |= HB_FLAG_NONFINITE;
-  if (flag && a.flags) a.flags[i] |= flag;
+  if (flag) a.flags[i] |= flag;
 }
 
 // stepHam iterated with the fixed RK4 stepper
-template <class S, bool FAST, int LAY>
-HB_DEV void hb_traj_step_rk4(const HbKArgs& a, long long i, const double* yin, const double* w, HbCtx& cx) {
+template <class S, bool FAST, int LAY, class I, int NST = 0>
+HB_DEV void hb_traj_step_rk4(const HbKArgs& a, I i, const double* yin, const double* w, HbCtx& cx) {
   constexpr int D = 2 * S::N;
   double y[D];
   int flag = 0;
@@ -1162,37 +879,40 @@ HB_DEV void hb_traj_step_rk4(const HbKArgs& a, long long i, const double* yin, c
     for (int c = 0; c < D; c++) y[c] = sm[c * B + threadIdx.x];
   } else {
     hb_copy<D>(yin, y);
-    for (int s = 0; s < a.nsteps; s++) hb_rk4_step<S, FAST>(cx, a.prm, w, y, a.dt, a.dt6, a.dth, flag);
+    if constexpr (NST == 1) hb_rk4_step<S, FAST>(cx, a.prm, w, y, a.dt, a.dt6, a.dth, flag);
+    else for (int s = 0; s < a.nsteps; s++) hb_rk4_step<S, FAST>(cx, a.prm, w, y, a.dt, a.dt6, a.dth, flag);
   }
   if (FAST && cx.oob) return;
-  hb_store<D>(a.out, i, a.N, hb_lay_of<LAY>(a), y);
-  hb_finish<D>(a, i, y, flag);
+  hb_store<D, I>(a.out, i, (I)a.N, hb_lay_of<LAY>(a), y);
+  hb_finish<D, I>(a, i, y, cx, flag);
 }
 // stepHam iterated with reference semantics: each step is a fresh adaptive solve over (0, dt)
-template <class S, bool FAST, int LAY>
-HB_DEV void hb_traj_step_rkf45(const HbKArgs& a, long long i, const double* yin, const double* w, HbCtx& cx) {
+template <class S, bool FAST, int LAY, class I>
+HB_DEV void hb_traj_step_rkf45(const HbKArgs& a, I i, const double* yin, const double* w, HbCtx& cx) {
   constexpr int D = 2 * S::N;
   double y[D];
   hb_copy<D>(yin, y);
   int flag = 0;
-  for (int s = 0; s < a.nsteps; s++) {
-    HbEvolve<D> e;
-    e.h = a.dt / 100;   // hi = (t1 - t0)/100, src/Numeric/Hamilton.hs:447
-    e.primed = false;
-    double t = 0.0;
-    hb_rkf45_to<S, FAST>(cx, a.prm, w, y, t, a.dt, e, flag);
+  if (a.dt > 0.0) {   // stepHam r with r <= 0 returns the Phase unchanged: hmatrix-gsl's `while (t < t1)` never runs
+    for (int s = 0; s < a.nsteps; s++) {
+      HbEvolve<D> e;
+      e.h = a.dt / 100;   // hi = (t1 - t0)/100, src/Numeric/Hamilton.hs:447
+      e.primed = false;
+      double t = 0.0;
+      hb_rkf45_to<S, FAST>(cx, a.prm, w, y, t, a.dt, e, flag);
+    }
   }
   if (FAST && cx.oob) return;
-  hb_store<D>(a.out, i, a.N, hb_lay_of<LAY>(a), y);
-  hb_finish<D>(a, i, y, flag);
+  hb_store<D, I>(a.out, i, (I)a.N, hb_lay_of<LAY>(a), y);
+  hb_finish<D, I>(a, i, y, cx, flag);
 }
 // evolveHam over a shared time grid; out[k] = batch at ts[k]
-template <class S, bool FAST, int LAY, bool ADAPTIVE>
-HB_DEV void hb_traj_evolve(const HbKArgs& a, long long i, const double* yin, const double* w, HbCtx& cx) {
+template <class S, bool FAST, int LAY, bool ADAPTIVE, class I>
+HB_DEV void hb_traj_evolve(const HbKArgs& a, I i, const double* yin, const double* w, HbCtx& cx) {
   constexpr int D = 2 * S::N;
   double y[D];
   hb_copy<D>(yin, y);
-  if (!FAST || !cx.oob) hb_store<D>(a.out, i, a.N, hb_lay_of<LAY>(a), y);   // row 0 is the initial state
+  if (!FAST || !cx.oob) hb_store<D, I>(a.out, i, (I)a.N, hb_lay_of<LAY>(a), y);   // row 0 is the initial state
   int flag = 0;
   HbEvolve<D> e;
   e.h = (a.ts[1] - a.ts[0]) / 100;
@@ -1209,28 +929,28 @@ HB_DEV void hb_traj_evolve(const HbKArgs& a, long long i, const double* yin, con
       t = tk;
     }
     if (FAST && cx.oob) return;   // rows written so far are rewritten by the slow retry (out never aliases in)
-    hb_store<D>(a.out + (long long)k * a.N * D, i, a.N, hb_lay_of<LAY>(a), y);
+    hb_store<D, I>(a.out + (size_t)k * (size_t)a.N * D, i, (I)a.N, hb_lay_of<LAY>(a), y);
   }
-  hb_finish<D>(a, i, y, flag);
+  hb_finish<D, I>(a, i, y, cx, flag);
 }
-template <class S, bool FAST, int LAY>
-HB_DEV void hb_traj_evolve_rk4(const HbKArgs& a, long long i, const double* yin, const double* w, HbCtx& cx) { hb_traj_evolve<S, FAST, LAY, false>(a, i, yin, w, cx); }
-template <class S, bool FAST, int LAY>
-HB_DEV void hb_traj_evolve_rkf45(const HbKArgs& a, long long i, const double* yin, const double* w, HbCtx& cx) { hb_traj_evolve<S, FAST, LAY, true>(a, i, yin, w, cx); }
+template <class S, bool FAST, int LAY, class I>
+HB_DEV void hb_traj_evolve_rk4(const HbKArgs& a, I i, const double* yin, const double* w, HbCtx& cx) { hb_traj_evolve<S, FAST, LAY, false, I>(a, i, yin, w, cx); }
+template <class S, bool FAST, int LAY, class I>
+HB_DEV void hb_traj_evolve_rkf45(const HbKArgs& a, I i, const double* yin, const double* w, HbCtx& cx) { hb_traj_evolve<S, FAST, LAY, true, I>(a, i, yin, w, cx); }
 
-template <class S, bool FAST, int LAY>
-HB_DEV void hb_traj_ham_eqs(const HbKArgs& a, long long i, const double* yin, const double* w, HbCtx& cx) {
+template <class S, bool FAST, int LAY, class I>
+HB_DEV void hb_traj_ham_eqs(const HbKArgs& a, I i, const double* yin, const double* w, HbCtx& cx) {
   constexpr int D = 2 * S::N;
   double y[D], dy[D];
   hb_copy<D>(yin, y);
   int flag = 0;
   hb_rhs<S, FAST>(cx, a.prm, w, y, dy, flag);
   if (FAST && cx.oob) return;
-  hb_store<D>(a.out, i, a.N, hb_lay_of<LAY>(a), dy);
-  hb_finish<D>(a, i, dy, flag);
+  hb_store<D, I>(a.out, i, (I)a.N, hb_lay_of<LAY>(a), dy);
+  hb_finish<D, I>(a, i, dy, cx, flag);
 }
-template <class S, bool FAST, int LAY>
-HB_DEV void hb_traj_to_phase(const HbKArgs& a, long long i, const double* yin, const double* w, HbCtx& cx) {   // Config [q, v] -> Phase [q, p]
+template <class S, bool FAST, int LAY, class I>
+HB_DEV void hb_traj_to_phase(const HbKArgs& a, I i, const double* yin, const double* w, HbCtx& cx) {   // Config [q, v] -> Phase [q, p]
   constexpr int D = 2 * S::N, N = S::N;
   double c[D], y[D];
   hb_copy<D>(yin, c);
@@ -1238,10 +958,10 @@ HB_DEV void hb_traj_to_phase(const HbKArgs& a, long long i, const double* yin, c
   for (int j = 0; j < N; j++) y[j] = c[j];
   hb_momenta<S, FAST>(cx, a.prm, w, c, c + N, y + N);
   if (FAST && cx.oob) return;
-  hb_store<D>(a.out, i, a.N, hb_lay_of<LAY>(a), y);
+  hb_store<D, I>(a.out, i, (I)a.N, hb_lay_of<LAY>(a), y);
 }
-template <class S, bool FAST, int LAY>
-HB_DEV void hb_traj_from_phase(const HbKArgs& a, long long i, const double* yin, const double* w, HbCtx& cx) {   // Phase [q, p] -> Config [q, v]
+template <class S, bool FAST, int LAY, class I>
+HB_DEV void hb_traj_from_phase(const HbKArgs& a, I i, const double* yin, const double* w, HbCtx& cx) {   // Phase [q, p] -> Config [q, v]
   constexpr int D = 2 * S::N, N = S::N;
   double y[D], c[D];
   hb_copy<D>(yin, y);
@@ -1251,12 +971,12 @@ HB_DEV void hb_traj_from_phase(const HbKArgs& a, long long i, const double* yin,
   for (int j = 0; j < N; j++) c[j] = y[j];
   hb_velocities<S, FAST, false>(cx, a.prm, w, y, y + N, c + N, U, flag);
   if (FAST && cx.oob) return;
-  hb_store<D>(a.out, i, a.N, hb_lay_of<LAY>(a), c);
-  hb_finish<D>(a, i, c, flag);
+  hb_store<D, I>(a.out, i, (I)a.N, hb_lay_of<LAY>(a), c);
+  hb_finish<D, I>(a, i, c, cx, flag);
 }
 // out4[i] = (keP, pe, hamiltonian, lagrangian)
-template <class S, bool FAST, int LAY>
-HB_DEV void hb_traj_energies(const HbKArgs& a, long long i, const double* yin, const double* w, HbCtx& cx) {
+template <class S, bool FAST, int LAY, class I>
+HB_DEV void hb_traj_energies(const HbKArgs& a, I i, const double* yin, const double* w, HbCtx& cx) {
   constexpr int D = 2 * S::N, N = S::N;
   double y[D], v[N];
   hb_copy<D>(yin, y);
@@ -1269,93 +989,106 @@ HB_DEV void hb_traj_energies(const HbKArgs& a, long long i, const double* yin, c
   for (int j = 0; j < N; j++) T = fma(v[j], y[N + j], T);
   T *= 0.5;   // (vs <.> ps) / 2, src/Numeric/Hamilton.hs:349
   double o[4] = {T, U, T + U, T - U};
-  hb_store<4>(a.out, i, a.N, a.layout == 2 ? 2 : 0, o);
-  hb_finish<4>(a, i, o, flag);
+  hb_store<4, I>(a.out, i, (I)a.N, a.layout == 2 ? 2 : 0, o);
+  hb_finish<4, I>(a, i, o, cx, flag);
 }
-template <class S, bool FAST, int LAY>
-HB_DEV void hb_traj_upos(const HbKArgs& a, long long i, const double* yin, const double* w, HbCtx& cx) {   // underlyingPos
+template <class S, bool FAST, int LAY, class I>
+HB_DEV void hb_traj_upos(const HbKArgs& a, I i, const double* yin, const double* w, HbCtx& cx) {   // underlyingPos
   constexpr int N = S::N, M = S::M;
   double q[N], x[M];
   (void)w;
   hb_copy<N>(yin, q);
   S::template pos<FAST>(cx, a.prm, q, x);
   if (FAST && cx.oob) return;
-  hb_store<M>(a.out, i, a.N, hb_lay_of<LAY>(a), x);
+  hb_store<M, I>(a.out, i, (I)a.N, hb_lay_of<LAY>(a), x);
 }
 
-// Kernel body = fast path inline + out-of-line slow retry for the rare out-of-domain trajectory.
-// DIN = doubles loaded per trajectory.  Launched as one resident wave (runtime.cpp launch()): a CTA stages the
-// sin/cos table once, then walks its trajectories grid-stride, prefetching the next Phase under the current compute.
-// Programmatic dependent launch: nothing before griddepcontrol.wait reads memory an upstream kernel may write.
+// Kernel body = fast path inline + out-of-line slow retry for the rare out-of-domain trajectory.  DIN = doubles loaded
+// per trajectory.
+//
+// Work distribution: the batch is cut into TILES of 32 consecutive trajectories (one warp instruction moves one tile:
+// contiguous 32 * 16n bytes); launched as ONE resident wave of G CTAs x W warps (runtime.cpp launch()), warp w of CTA b
+// walks tiles b + G (w + W r), r = 0, 1, ... — every round spreads over all CTAs, so whatever the batch size the last,
+// partial round leaves the same number of busy warps on every SM (a grid-stride loop over thread indices piles the
+// remainder onto the first CTAs).  Trajectory indices are 32-bit (the host splits batches >= 2^31).
+// Per launch, in this order:  griddepcontrol.launch_dependents (the next kernel of the stream may start its own
+// prologue as soon as SM resources free up)  ->  sin/cos table staging by ONE cp.async.bulk (TMA) per CTA  ->  L2
+// prefetch of the warp's first two tiles  ->  griddepcontrol.wait (everything above touches only constant data or
+// prefetches into the coherent L2, so it overlaps the previous kernel's tail)  ->  the tile loop, which loads the
+// thread's next Phase under the current trajectory's arithmetic into the idle one of two register buffers.
+#define HB_PROCESS_(NAME, IDX, YBUF)                                                                       \
+  {                                                                                                        \
+    HbCtx cx;                                                                                              \
+    cx.tab_s = tab_s;                                                                                      \
+    hb_ctx_reset(cx);                                                                                      \
+    HB_TRAJ_CALL_##NAME(IDX, YBUF)                                                                         \
+    if (cx.oob) hb_slow_##NAME<S>(a, (long long)(IDX));                                                    \
+  }
+#define HB_TRAJ_CALL_step_rk4(IDX, YBUF) hb_traj_step_rk4<S, true, LAY, unsigned, NST>(a, IDX, YBUF, w, cx);
+#define HB_TRAJ_CALL_step_rkf45(IDX, YBUF) hb_traj_step_rkf45<S, true, LAY, unsigned>(a, IDX, YBUF, w, cx);
+#define HB_TRAJ_CALL_evolve_rk4(IDX, YBUF) hb_traj_evolve_rk4<S, true, LAY, unsigned>(a, IDX, YBUF, w, cx);
+#define HB_TRAJ_CALL_evolve_rkf45(IDX, YBUF) hb_traj_evolve_rkf45<S, true, LAY, unsigned>(a, IDX, YBUF, w, cx);
+#define HB_TRAJ_CALL_ham_eqs(IDX, YBUF) hb_traj_ham_eqs<S, true, LAY, unsigned>(a, IDX, YBUF, w, cx);
+#define HB_TRAJ_CALL_to_phase(IDX, YBUF) hb_traj_to_phase<S, true, LAY, unsigned>(a, IDX, YBUF, w, cx);
+#define HB_TRAJ_CALL_from_phase(IDX, YBUF) hb_traj_from_phase<S, true, LAY, unsigned>(a, IDX, YBUF, w, cx);
+#define HB_TRAJ_CALL_energies(IDX, YBUF) hb_traj_energies<S, true, LAY, unsigned>(a, IDX, YBUF, w, cx);
+#define HB_TRAJ_CALL_upos(IDX, YBUF) hb_traj_upos<S, true, LAY, unsigned>(a, IDX, YBUF, w, cx);
 #define HB_KERNEL_BODY(NAME, DIN_EXPR)                                                                     \
   template <class S>                                                                                       \
   __device__ __noinline__ void hb_slow_##NAME(const HbKArgs& a, long long i) {                             \
     constexpr int DIN = DIN_EXPR;                                                                          \
     double w[S::M], yin[DIN];                                                                              \
     S::inertia(a.prm, w);                                                                                  \
-    hb_load<DIN>(a.in, i, a.N, a.layout, yin);                                                             \
+    hb_load<DIN, long long>(a.in, i, a.N, a.layout, yin);                                                  \
     HbCtx cx;                                                                                              \
     cx.tab_s = 0;                                                                                          \
-    cx.oob = 0;                                                                                            \
-    hb_traj_##NAME<S, false, -1>(a, i, yin, w, cx);                                                            \
+    hb_ctx_reset(cx);                                                                                      \
+    hb_traj_##NAME<S, false, -1, long long>(a, i, yin, w, cx);                                             \
   }                                                                                                        \
-  template <class S, int LAY>                                                                              \
-  HB_DEV void hb_body_##NAME(const HbKArgs& a, double2* tab) {                                                           \
+  template <class S, int LAY, int NST = 0>                                                                 \
+  HB_DEV void hb_body_##NAME(const HbKArgs& a, HbTab* tab) {                                               \
     constexpr int DIN = DIN_EXPR;                                                                          \
-    const long long stride = (long long)gridDim.x * blockDim.x;                                            \
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;                                        \
-    /* prologue that touches nothing an upstream kernel writes: let the next launch in the stream start  */ \
-    /* (programmatic dependent launch) and stage the table while the previous kernel drains              */ \
+    const unsigned N = (unsigned)a.N;                                                                      \
+    const unsigned istride = gridDim.x * blockDim.x;   /* trajectories per round */                        \
+    unsigned i = (blockIdx.x + gridDim.x * (threadIdx.x >> 5)) * 32u + (threadIdx.x & 31u);                \
+    const int lay = hb_lay_of<LAY>(a);                                                                     \
     HB_PDL_LAUNCH_DEPENDENTS();                                                                            \
-    if constexpr (S::TRIG) hb_tab_init(tab);                                                               \
+    if constexpr (S::TRIG) hb_tab_issue(tab);                                                              \
+    if constexpr (HB_PRE_L2) {                                                                             \
+      if (i < N) hb_prefetch_l2<DIN, unsigned>(a.in, i, N, lay);                                           \
+      if (i + istride < N) hb_prefetch_l2<DIN, unsigned>(a.in, i + istride, N, lay);                       \
+    }                                                                                                      \
+    if constexpr (S::TRIG) hb_tab_wait(tab);                                                               \
     HB_PDL_WAIT();                                                                                         \
-    double yin[DIN];                                                                                       \
-    if (i < a.N) hb_load<DIN>(a.in, i, a.N, hb_lay_of<LAY>(a), yin);                                                \
     double w[S::M];                                                                                        \
     S::inertia(a.prm, w);                                                                                  \
-    const unsigned tab_s = (unsigned)__cvta_generic_to_shared(tab) + ((threadIdx.x & (HB_SC_REP - 1)) << 4); \
-    if constexpr (HB_UNROLL2 && DIN <= 8) {   /* experiment: two copies of the step, the Phase buffers swap roles (no copy) */ \
-      double yb[DIN];                                                                                      \
-      while (i < a.N) {                                                                                    \
-        {                                                                                                  \
-          HbCtx cx;                                                                                        \
-          cx.tab_s = tab_s;                                                                                \
-          cx.oob = 0;                                                                                      \
-          if (i + stride < a.N) hb_load<DIN>(a.in, i + stride, a.N, hb_lay_of<LAY>(a), yb);                \
-          hb_traj_##NAME<S, true, LAY>(a, i, yin, w, cx);                                                  \
-          if (cx.oob) hb_slow_##NAME<S>(a, i);                                                             \
-          i += stride;                                                                                     \
-        }                                                                                                  \
-        if (!(i < a.N)) break;                                                                             \
-        {                                                                                                  \
-          HbCtx cx;                                                                                        \
-          cx.tab_s = tab_s;                                                                                \
-          cx.oob = 0;                                                                                      \
-          if (i + stride < a.N) hb_load<DIN>(a.in, i + stride, a.N, hb_lay_of<LAY>(a), yin);               \
-          hb_traj_##NAME<S, true, LAY>(a, i, yb, w, cx);                                                   \
-          if (cx.oob) hb_slow_##NAME<S>(a, i);                                                             \
-          i += stride;                                                                                     \
-        }                                                                                                  \
+    const unsigned tab_s = hb_smem_addr(tab);                                                              \
+    bool more = i < N;                                                                                     \
+    if constexpr (HB_PINGPONG && DIN <= 8) {                                                               \
+      double ya[DIN], yb[DIN];                                                                             \
+      if (more) hb_load<DIN, unsigned>(a.in, i, N, lay, ya);                                               \
+      while (more) {                                                                                       \
+        unsigned inext = i + istride;                                                                      \
+        more = inext < N;                                                                                  \
+        if (more) hb_load<DIN, unsigned>(a.in, inext, N, lay, yb);                                         \
+        HB_PROCESS_(NAME, i, ya)                                                                           \
+        if (!more) break;                                                                                  \
+        i = inext;                                                                                         \
+        inext = i + istride;                                                                               \
+        more = inext < N;                                                                                  \
+        if (more) hb_load<DIN, unsigned>(a.in, inext, N, lay, ya);                                         \
+        HB_PROCESS_(NAME, i, yb)                                                                           \
+        i = inext;                                                                                         \
       }                                                                                                    \
-      return;                                                                                              \
-    }                                                                                                      \
-    while (i < a.N) {                                                                                      \
-      HbCtx cx;                                                                                            \
-      cx.tab_s = tab_s;                                                                                    \
-      cx.oob = 0;                                                                                          \
-      if constexpr (DIN <= 8 && !HB_L2_PREFETCH) {   /* small state: prefetch the thread's next trajectory under this one's compute */ \
-        double ycur[DIN];                                                                                  \
-        hb_copy<DIN>(yin, ycur);                                                                           \
-        if (i + stride < a.N) hb_load<DIN>(a.in, i + stride, a.N, hb_lay_of<LAY>(a), yin);                          \
-        if constexpr (HB_L2_AHEAD > 0) { if (i + (HB_L2_AHEAD + 1) * stride < a.N) hb_prefetch_l2<DIN>(a.in, i + (HB_L2_AHEAD + 1) * stride, a.N, hb_lay_of<LAY>(a)); } \
-        hb_traj_##NAME<S, true, LAY>(a, i, ycur, w, cx);                                                        \
-      } else {                                                                                             \
-        if constexpr (HB_L2_PREFETCH) { if (i + stride < a.N) hb_prefetch_l2<DIN>(a.in, i + stride, a.N, hb_lay_of<LAY>(a)); } \
-        hb_traj_##NAME<S, true, LAY>(a, i, yin, w, cx);                                                         \
+    } else {                                                                                               \
+      double yin[DIN];                                                                                     \
+      while (more) {                                                                                       \
+        hb_load<DIN, unsigned>(a.in, i, N, lay, yin);                                                      \
+        if constexpr (HB_PRE_L2) { if (i + 2 * istride < N) hb_prefetch_l2<DIN, unsigned>(a.in, i + 2 * istride, N, lay); } \
+        HB_PROCESS_(NAME, i, yin)                                                                          \
+        i += istride;                                                                                      \
+        more = i < N;                                                                                      \
       }                                                                                                    \
-      if (cx.oob) hb_slow_##NAME<S>(a, i);                                                                 \
-      i += stride;                                                                                         \
-      if constexpr (DIN > 8 || HB_L2_PREFETCH) { if (i < a.N) hb_load<DIN>(a.in, i, a.N, hb_lay_of<LAY>(a), yin); } \
     }                                                                                                      \
   }
 HB_KERNEL_BODY(step_rk4, 2 * S::N)
@@ -1402,34 +1135,41 @@ HB_DEV void hb_body_init_random(const HbKArgs& a) {
 #define HB_K_UPOS 8
 #define HB_K_COUNT 9
 
-#if defined(HB_MINB_RK4) && HB_MINB_RK4 == 0   // tuning experiments: no occupancy request at all
-#define HB_LB_RK4(SYS) __launch_bounds__(HB_MAXBLOCK_OF(SYS::N))
-#elif defined(HB_MINB_RK4)                      // tuning experiments: explicit register cap for the RK4 step kernel
+#ifdef HB_MINB_RK4                              // tuning experiments: explicit register cap for the RK4 step kernel
 #define HB_LB_RK4(SYS) __launch_bounds__(HB_MAXBLOCK_OF(SYS::N), HB_MINB_RK4)
 #else   // default: no occupancy request — every explicit one measured slower at one step per launch (profiles/r1p)
 #define HB_LB_RK4(SYS) __launch_bounds__(HB_MAXBLOCK_OF(SYS::N))
 #endif
 
-// Instantiates per-system __global__ kernels with C linkage names PFX_<kind>.  The sin/cos table is declared here, once per
-// kernel, and handed to the body.
-#define HB_TAB_DECL(SYS) __shared__ double2 hb_tab[SYS::TRIG ? HB_SC_N * HB_SC_REP : 1]
-#define HB_DEFINE_KERNEL_step_rk4(SYS, PFX) extern "C" __global__ void HB_LB_RK4(SYS) PFX##_step_rk4(const __grid_constant__ HbKArgs a) { \
-    HB_TAB_DECL(SYS);                                                                                                                      \
-    if constexpr (HB_LAYSPEC && SYS::N < HB_BIG_N) {   /* (large systems: the step dwarfs the bookkeeping; one instance keeps compile time) */ \
-      if (a.layout == 1) hb_body_step_rk4<SYS, -1>(a, hb_tab); else hb_body_step_rk4<SYS, 0>(a, hb_tab);                                  \
-    } else {                                                                                                                               \
-      hb_body_step_rk4<SYS, -1>(a, hb_tab);                                                                                                \
+// Instantiates per-system __global__ kernels with C linkage names PFX_<kind>.  The sin/cos table image is declared here,
+// once per kernel, and handed to the body (systems without sin/cos reserve nothing).
+#define HB_TAB_DECL(SYS)                                                                          \
+  __shared__ __align__(128) unsigned char hb_tab_raw[SYS::TRIG ? sizeof(HbTab) : 16];             \
+  HbTab* hb_tab = reinterpret_cast<HbTab*>(hb_tab_raw)
+// step kernels: one instance per layout class, picked once per launch (large systems: the step dwarfs the bookkeeping; one
+// instance keeps compile time)
+#define HB_DEFINE_KERNEL_L(SYS, PFX, KIND, LB, NST1)                                              \
+  extern "C" __global__ void LB PFX##_##KIND(const __grid_constant__ HbKArgs a) {                 \
+    HB_TAB_DECL(SYS);                                                                             \
+    if constexpr (HB_LAYSPEC && SYS::N < HB_BIG_N) {                                              \
+      if (a.layout != 0) hb_body_##KIND<SYS, -1>(a, hb_tab);                                      \
+      else if (NST1 && a.nsteps == 1) hb_body_##KIND<SYS, 0, NST1>(a, hb_tab);                    \
+      else hb_body_##KIND<SYS, 0>(a, hb_tab);                                                     \
+    } else {                                                                                      \
+      hb_body_##KIND<SYS, -1>(a, hb_tab);                                                         \
     } }
+#define HB_DEFINE_KERNEL_step_rk4(SYS, PFX) HB_DEFINE_KERNEL_L(SYS, PFX, step_rk4, HB_LB_RK4(SYS), 1)
 #define HB_DEFINE_KERNEL_X(SYS, PFX, KIND) extern "C" __global__ void __launch_bounds__(HB_MAXBLOCK_OF(SYS::N)) PFX##_##KIND(const __grid_constant__ HbKArgs a) { HB_TAB_DECL(SYS); hb_body_##KIND<SYS, -1>(a, hb_tab); }
 #ifdef HB_MINB_RKF45   // tuning experiments: register cap for the adaptive kernels
-#define HB_DEFINE_KERNEL_Y(SYS, PFX, KIND) extern "C" __global__ void __launch_bounds__(HB_MAXBLOCK_OF(SYS::N), HB_MINB_RKF45) PFX##_##KIND(const __grid_constant__ HbKArgs a) { HB_TAB_DECL(SYS); hb_body_##KIND<SYS, -1>(a, hb_tab); }
+#define HB_LB_RKF45(SYS) __launch_bounds__(HB_MAXBLOCK_OF(SYS::N), HB_MINB_RKF45)
 #else
 // The adaptive kernels keep six stage vectors live and reach 200+ registers (2 CTAs/SM: two warps per scheduler cannot
 // cover the 8-clock FP64 latency).  Capping small systems at 128 registers (4 CTAs/SM) spills a few stage vectors to
 // local memory and still wins: double pendulum +10 %, triple pendulum +11 % (profiles/r1z/ab_rkf45_regs.txt).
-#define HB_DEFINE_KERNEL_Y(SYS, PFX, KIND) extern "C" __global__ void __launch_bounds__(HB_MAXBLOCK_OF(SYS::N), (SYS::N <= 3 ? 4 : 0)) PFX##_##KIND(const __grid_constant__ HbKArgs a) { HB_TAB_DECL(SYS); hb_body_##KIND<SYS, -1>(a, hb_tab); }
+#define HB_LB_RKF45(SYS) __launch_bounds__(HB_MAXBLOCK_OF(SYS::N), (SYS::N <= 3 ? 512 / HB_MAXBLOCK_OF(SYS::N) : 0))
 #endif
-#define HB_DEFINE_KERNEL_step_rkf45(SYS, PFX) HB_DEFINE_KERNEL_Y(SYS, PFX, step_rkf45)
+#define HB_DEFINE_KERNEL_Y(SYS, PFX, KIND) extern "C" __global__ void HB_LB_RKF45(SYS) PFX##_##KIND(const __grid_constant__ HbKArgs a) { HB_TAB_DECL(SYS); hb_body_##KIND<SYS, -1>(a, hb_tab); }
+#define HB_DEFINE_KERNEL_step_rkf45(SYS, PFX) HB_DEFINE_KERNEL_L(SYS, PFX, step_rkf45, HB_LB_RKF45(SYS), 0)
 #define HB_DEFINE_KERNEL_evolve_rk4(SYS, PFX) HB_DEFINE_KERNEL_X(SYS, PFX, evolve_rk4)
 #define HB_DEFINE_KERNEL_evolve_rkf45(SYS, PFX) HB_DEFINE_KERNEL_Y(SYS, PFX, evolve_rkf45)
 #define HB_DEFINE_KERNEL_ham_eqs(SYS, PFX) HB_DEFINE_KERNEL_X(SYS, PFX, ham_eqs)

@@ -10,6 +10,7 @@
 #include <unistd.h>
 
 #include <cmath>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -40,6 +41,7 @@ static const char* const KERNEL_KINDS[K_COUNT] = {"step_rk4", "step_rkf45", "evo
 #define HB_WSTORE_MAXD 8   // must match engine/hb_engine.cuh
 #define HB_DYN_DOUBLES(NCOORD, NE_) ((NCOORD) >= HB_BIG_N ? 3 * 2 * (NCOORD) + (NE_) : 0)
 #define HB_MAXBLOCK_OF(NCOORD) HB_BLOCK_OF(NCOORD)
+#define HB_MAX_LAUNCH_N ((int64_t)0x7C000000)   // 2^31 - 2^26: i + (trajectories per round) stays below 2^32 in the kernels
 
 // from aot_kernels.cu
 extern "C" const void* hb_aot_kernel(int builtin, int kernel_id);
@@ -48,6 +50,7 @@ extern "C" int hb_aot_dyn_doubles(int builtin);
 extern "C" size_t hb_aot_kargs_size(void);
 // from gen/engine_embed.inc (the engine header as a string, for NVRTC)
 extern const char hb_engine_src[];
+extern const char hb_sincos_tab_src[];
 
 namespace {
 
@@ -178,6 +181,7 @@ bool nvrtc_compile(const std::string& src, const std::string& arch, std::vector<
   if (!dir.empty()) {
     Hash128 h;
     h.add(hb_engine_src, std::strlen(hb_engine_src));
+    h.add(hb_sincos_tab_src, std::strlen(hb_sincos_tab_src));
     h.add(src);
     h.add(arch);
     if (const char* e = std::getenv("HB_JIT_DEFINES")) h.add(e, std::strlen(e));
@@ -197,9 +201,9 @@ bool nvrtc_compile_uncached(const std::string& src, const std::string& arch, std
   std::lock_guard<std::mutex> lk(g_nvrtc_mu);
   if (!g_nvrtc.load()) { log = g_nvrtc.err; return false; }
   nvrtcProgram prog;
-  const char* hdr_src[] = {hb_engine_src};
-  const char* hdr_name[] = {"hb_engine.cuh"};
-  nvrtcResult r = g_nvrtc.CreateProgram(&prog, src.c_str(), "hb_jit_system.cu", 1, hdr_src, hdr_name);
+  const char* hdr_src[] = {hb_engine_src, hb_sincos_tab_src};
+  const char* hdr_name[] = {"hb_engine.cuh", "hb_sincos_tab.cuh"};
+  nvrtcResult r = g_nvrtc.CreateProgram(&prog, src.c_str(), "hb_jit_system.cu", 2, hdr_src, hdr_name);
   if (r != NVRTC_SUCCESS) { log = std::string("nvrtcCreateProgram: ") + g_nvrtc.GetErrorString(r); return false; }
   std::string a = "--gpu-architecture=" + arch;
   std::vector<std::string> extra;   // HB_JIT_DEFINES="HB_MINB_RK4=8,FOO=1": tuning experiments without a rebuild
@@ -369,22 +373,27 @@ int resident_ctas(const void* fn, int block, size_t dyn_smem) {
 }
 
 // Launch policy.  Batches that fill the chip run as ONE resident wave (grid = SMs x occupancy, 148 x k on B200): every CTA
-// stages the sin/cos table once and walks its trajectories with a grid-stride loop that prefetches the next Phase under
-// the current step's arithmetic.  Every launch carries the programmatic-stream-serialization attribute: the kernels call
-// griddepcontrol.launch_dependents first thing and griddepcontrol.wait before their first global read, so in a stream (or
-// captured graph) of back-to-back steps the next kernel's launch latency and table staging hide under this kernel's tail.
+// stages the sin/cos table once (one bulk copy) and its warps walk tiles of 32 trajectories, b + G (w + W r) — every round
+// of tiles spreads over all CTAs, so the last partial round is balanced over the SMs (engine/hb_engine.cuh HB_KERNEL_BODY).
+// Every launch carries the programmatic-stream-serialization attribute: the kernels call griddepcontrol.launch_dependents
+// first thing and griddepcontrol.wait before their first global read, so in a stream (or captured graph) of back-to-back
+// steps the next kernel's launch latency, table staging and first L2 prefetches hide under this kernel's tail.
+// The kernels index trajectories with 32 bits: callers (run_batch) hand at most HB_MAX_LAUNCH_N trajectories per launch.
 hb_status launch(const void* fn, const HbKArgs& a, long long work_items, cudaStream_t st, int block = HB_BLOCK, int max_block = HB_BLOCK,
                  int dyn_doubles = 0) {
   if (work_items <= 0) return HB_OK;
   static const int block_env = [] { const char* e = std::getenv("HB_BLOCK"); int t = e ? std::atoi(e) : 0; return (t >= 32 && t <= 1024 && t % 32 == 0) ? t : 0; }();
-  if (block_env && block_env <= max_block && dyn_doubles == 0) block = block_env;   // (shared-memory layouts assume HB_BLOCK_OF)
+  // experiment knob: small systems only (shared-memory layouts of large ones assume HB_BLOCK_OF); a size above the kernel's
+  // __launch_bounds__ (HB_BLOCK_SMALL at compile time) makes the launch fail with an error, never run wrongly
+  (void)max_block;
+  if (block_env && dyn_doubles == 0) block = block_env;
   static const double waves_env = [] { const char* e = std::getenv("HB_GRID_WAVES"); double t = e ? std::atof(e) : 0.0; return (t > 0 && t <= 4096) ? t : 0.0; }();
   static const bool pdl = std::getenv("HB_NO_PDL") == nullptr;
   long long blocks = (work_items + block - 1) / block;
   const size_t dyn_smem = (size_t)dyn_doubles * sizeof(double) * block;
   const int slots = resident_ctas(fn, block, dyn_smem);
   if (slots < 0) return fail(HB_ERR_CUDA, "kernel needs more dynamic shared memory than the device offers");
-  const long long cap = (long long)((double)slots * (waves_env > 0 ? waves_env : 2.0));
+  const long long cap = (long long)((double)slots * (waves_env > 0 ? waves_env : 1.0));
   if (slots > 0 && blocks > cap) blocks = cap;
   if (blocks > 0x7fffffffLL) blocks = 0x7fffffffLL;
   void* args[] = {(void*)&a};
@@ -416,6 +425,20 @@ hb_status run_batch(const hb_system* sys, int kid, HbKArgs a, int64_t N, hb_mems
   if (N < 0) return fail(HB_ERR_INVALID, "negative batch size");
   if (N == 0) return HB_OK;
   if (!in || !out) return fail(HB_ERR_INVALID, "null batch pointer");
+  // array-of-records pointers are cast to double2 by the kernels: a misaligned pointer would be a sticky device fault
+  if (a.layout == HB_LAYOUT_AOS && (((uintptr_t)in | (uintptr_t)out) & 15) != 0 && in_d % 2 == 0 && out_d % 2 == 0)
+    return fail(HB_ERR_INVALID, "array-of-Phases batches must be 16-byte aligned");
+  if ((((uintptr_t)in | (uintptr_t)out) & 7) != 0 || ((uintptr_t)flags & 3) != 0) return fail(HB_ERR_INVALID, "misaligned batch pointer");
+  if (N > HB_MAX_LAUNCH_N) {   // the kernels index trajectories with 32 bits: larger batches go in slices
+    if (a.layout != HB_LAYOUT_AOS || out_batches != 1)
+      return fail(HB_ERR_UNSUPPORTED, "more than 2^31 - 2^26 trajectories per call need the array-of-Phases layout (and evolve calls must be sliced by the caller)");
+    for (int64_t i0 = 0; i0 < N; i0 += HB_MAX_LAUNCH_N) {
+      const int64_t n = N - i0 < HB_MAX_LAUNCH_N ? N - i0 : HB_MAX_LAUNCH_N;
+      hb_status rs = run_batch(sys, kid, a, n, mem, in + (size_t)i0 * in_d, in_d, out + (size_t)i0 * out_d, out_d, 1, flags ? flags + i0 : nullptr, ts, s, stream);
+      if (rs) return rs;
+    }
+    return HB_OK;
+  }
   hb_status rc = need_device();
   if (rc) return rc;
   const void* fn = nullptr;
@@ -717,7 +740,8 @@ hb_status hb_batch_step(const hb_system* sys, hb_integrator integ, double dt, in
   if (bad_layout(layout)) return fail(HB_ERR_INVALID, "bad layout");
   if (integ != HB_INTEG_RK4 && integ != HB_INTEG_RKF45_GSL) return fail(HB_ERR_INVALID, "unknown integrator");
   if (nsteps < 0) return fail(HB_ERR_INVALID, "negative nsteps");
-  if (integ == HB_INTEG_RKF45_GSL && !(dt > 0.0)) return fail(HB_ERR_INVALID, "RKF45_GSL needs dt > 0");
+  // RKF45_GSL with dt <= 0: the kernel returns every Phase unchanged, as `stepHam r` does for r <= 0 (hmatrix-gsl's
+  // `while (t < t1)` loop never runs)
   HbKArgs a; fill_params(sys, a); a.layout = layout; a.dt = dt; a.dt6 = dt / 6.0; a.dth = 0.5 * dt; a.nsteps = nsteps;
   return run_batch(sys, integ == HB_INTEG_RK4 ? K_STEP_RK4 : K_STEP_RKF45, a, N, mem, y_in, 2 * sys->n, y_out, 2 * sys->n, 1, flags,
                    nullptr, 0, stream);

@@ -528,7 +528,8 @@ bool generate_system(const SystemSpec& spec, const std::string& name, GeneratedS
 
 std::string jit_translation_unit(const GeneratedSystem& g, const std::string& prefix, const std::string& kind) {
   const std::string macro = kind.empty() ? "HB_DEFINE_KERNELS" : "HB_DEFINE_KERNEL_" + kind;
-  return "#include \"hb_engine.cuh\"\n" + g.source + macro + "(" + g.name + ", " + prefix + ")\n";
+  // large systems: the dynamic shared memory of the RK vectors leaves room for the 8 KB sin/cos table only (HB_BIG_N = 8)
+  return std::string(g.n >= 8 ? "#define HB_SC_LOG2 9\n" : "") + "#include \"hb_engine.cuh\"\n" + g.source + macro + "(" + g.name + ", " + prefix + ")\n";
 }
 
 }  // namespace hb

@@ -1,0 +1,72 @@
+"""Round-2 A/B of engine compile-time switches on the NVRTC build of a built-in definition (same engine source as the
+ahead-of-time kernels).  One variant per subprocess: HB_JIT_DEFINES / HB_BLOCK / HB_GRID_WAVES are read at library load.
+  python profiles/exp/exp_r2_ab.py run <system> [log2N]       (worker)
+  python profiles/exp/exp_r2_ab.py sweep <system> [log2N]     (driver: prints one line per variant)
+Timing: a CUDA graph of K one-step launches over a ring of 9 (in, out) buffer pairs (inputs larger than L2, as bench.py),
+a graph of K launches ping-ponging between two buffers (a real stepping loop: L2-resident), and 16 steps fused per launch."""
+import os, subprocess, sys
+VARIANTS = [
+    ("default", {}),
+    ("2 waves", {"HB_GRID_WAVES": "2"}),
+    ("table 512 (13-instr sincos)", {"HB_JIT_DEFINES": "HB_SC_LOG2=9"}),
+    ("Cody-Waite 2 terms", {"HB_JIT_DEFINES": "HB_SC_CW2=1"}),
+    ("no ping-pong", {"HB_JIT_DEFINES": "HB_PINGPONG=0"}),
+    ("no L2 prefetch before the wait", {"HB_JIT_DEFINES": "HB_PRE_L2=0"}),
+    ("table staged by loads, not cp.async.bulk", {"HB_JIT_DEFINES": "HB_TAB_BULK=0"}),
+    ("no PDL", {"HB_NO_PDL": "1"}),
+    ("CTA 256", {"HB_JIT_DEFINES": "HB_BLOCK_SMALL=256", "HB_BLOCK": "256"}),
+    ("CTA 320", {"HB_JIT_DEFINES": "HB_BLOCK_SMALL=320", "HB_BLOCK": "320"}),
+    ("CTA 640", {"HB_JIT_DEFINES": "HB_BLOCK_SMALL=640", "HB_BLOCK": "640"}),
+    ("CTA 64", {"HB_BLOCK": "64"}),
+    ("min 6 CTAs/SM", {"HB_JIT_DEFINES": "HB_MINB_RK4=6"}),
+]
+def worker(name, log2n):
+    sys.path.insert(0, ".")
+    import torch
+    import hamilton_b200 as hb
+    from tests.common import BOXES
+    N = 1 << log2n
+    sid, lo, hi = BOXES[name]
+    s = hb.systems.from_def(hb.systems.DEFS[sid]())
+    ring = 9
+    ins = [s.batch_init_random(7 + r, 0, N, lo, hi) for r in range(ring)]
+    outs = [torch.empty_like(b) for b in ins]
+    K = 200
+    def timed(fn, reps=3):
+        best = 1e30
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return best
+    def graph_of(body):
+        g = torch.cuda.CUDAGraph()
+        st = torch.cuda.Stream()
+        st.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(st):
+            with torch.cuda.graph(g, stream=st):
+                body()
+        torch.cuda.current_stream().wait_stream(st)
+        g.replay(); torch.cuda.synchronize()
+        return g
+    for i in range(3): s.batch_step(ins[i], 0.01, 1, out=outs[i])
+    torch.cuda.synchronize()
+    g_ring = graph_of(lambda: [s.batch_step(ins[i % ring], 0.01, 1, out=outs[i % ring]) for i in range(K)])
+    a, b = ins[0].clone(), outs[0]
+    g_chain = graph_of(lambda: [s.batch_step(a if i % 2 == 0 else b, 0.01, 1, out=b if i % 2 == 0 else a) for i in range(K)])
+    t_ring = timed(g_ring.replay) / K
+    t_chain = timed(g_chain.replay) / K
+    t_16 = timed(lambda: [s.batch_step(ins[i % ring], 0.01, 16, out=outs[i % ring]) for i in range(8)]) / 8
+    print("RESULT ring %.3f us/launch (%.3e steps/s)  chain %.3f us/launch (%.3e)  fused16 %.3e steps/s" %
+          (t_ring * 1e3, N / t_ring * 1e3, t_chain * 1e3, N / t_chain * 1e3, N * 16 / t_16 * 1e3))
+if sys.argv[1] == "run":
+    worker(sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 20)
+else:
+    name, log2n = sys.argv[2], (sys.argv[3] if len(sys.argv) > 3 else "20")
+    only = sys.argv[4].split(",") if len(sys.argv) > 4 else None
+    for label, env in VARIANTS:
+        if only and not any(o in label for o in only): continue
+        e = dict(os.environ); e.update(env)
+        p = subprocess.run([sys.executable, __file__, "run", name, log2n], env=e, capture_output=True, text=True, timeout=600)
+        res = [l for l in p.stdout.split("\n") if l.startswith("RESULT")]
+        print("%-42s %s" % (label, res[0][7:] if res else "FAILED: " + (p.stderr.strip().split("\n") or ["?"])[-1][:200]), flush=True)

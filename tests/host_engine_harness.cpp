@@ -46,7 +46,9 @@ using std::asinh; using std::acosh; using std::atanh; using std::sin; using std:
 typedef SYS_NAME S;
 static constexpr int N = S::N, D = 2 * S::N;
 
-static HbCtx ctx() { HbCtx cx; cx.tab_s = 0; cx.oob = 0; return cx; }
+static HbCtx ctx() { HbCtx cx; cx.tab_s = 0; hb_ctx_reset(cx); return cx; }
+// HB_FLAG_* bits (integrator flags + deferred pivot test) | "left the fast domain" << 8
+static int result(const HbCtx& cx, int flag) { return hb_ctx_flags(cx, flag) | (cx.oob ? 1 << 8 : 0); }
 
 extern "C" void dims(int* o) { o[0] = S::M; o[1] = S::N; o[2] = S::SYMH ? 1 : 0; o[3] = N >= HB_BIG_N ? 1 : 0; }
 
@@ -57,7 +59,7 @@ extern "C" int ham_eqs(const double* prm, const double* y, double* dy) {
   HbCtx cx = ctx();
   int flag = 0;
   hb_rhs<S, true>(cx, prm, w, y, dy, flag);
-  return flag | (int)(cx.oob << 8);
+  return result(cx, flag);
 }
 extern "C" int rk4_steps(const double* prm, double* y_io, double dt, int nsteps) {
   double w[S::M];
@@ -76,7 +78,7 @@ extern "C" int rk4_steps(const double* prm, double* y_io, double dt, int nsteps)
     for (int s = 0; s < nsteps; s++) hb_rk4_step<S, true>(cx, prm, w, y, dt, dt / 6.0, 0.5 * dt, flag);
     for (int c = 0; c < D; c++) y_io[c] = y[c];
   }
-  return flag | (int)(cx.oob << 8);
+  return result(cx, flag);
 }
 // stepHam iterated: a fresh GSL-RKF45 solve over (0, dt) per step, exactly as hb_traj_step_rkf45 does
 extern "C" int rkf45_steps(const double* prm, double* y_io, double dt, int nsteps) {
@@ -94,7 +96,7 @@ extern "C" int rkf45_steps(const double* prm, double* y_io, double dt, int nstep
     hb_rkf45_to<S, true>(cx, prm, w, y, t, dt, e, flag);
   }
   for (int c = 0; c < D; c++) y_io[c] = y[c];
-  return flag | (int)(cx.oob << 8);
+  return result(cx, flag);
 }
 // evolveHam over a grid (h and the FSAL derivative carried), as hb_traj_evolve<ADAPTIVE> does; out = s rows of D
 extern "C" int evolve_rkf45(const double* prm, const double* y0, const double* ts, int s, double* out) {
@@ -112,7 +114,7 @@ extern "C" int evolve_rkf45(const double* prm, const double* y0, const double* t
     hb_rkf45_to<S, true>(cx, prm, w, y, t, ts[k], e, flag);
     for (int c = 0; c < D; c++) out[k * D + c] = y[c];
   }
-  return flag | (int)(cx.oob << 8);
+  return result(cx, flag);
 }
 extern "C" int config_maps(const double* prm, const double* q, const double* v, double* p_out, double* v_back, double* U) {
   double w[S::M];
@@ -121,17 +123,17 @@ extern "C" int config_maps(const double* prm, const double* q, const double* v, 
   int flag = 0;
   hb_momenta<S, true>(cx, prm, w, q, v, p_out);
   hb_velocities<S, true, true>(cx, prm, w, q, p_out, v_back, *U, flag);
-  return flag | (int)(cx.oob << 8);
+  return result(cx, flag);
 }
 // primitives
-extern "C" int sincos_fast(double x, double* s, double* c) { HbCtx cx = ctx(); hb_sincos<true>(cx, x, s, c); return (int)cx.oob; }
+extern "C" int sincos_fast(double x, double* s, double* c) { HbCtx cx = ctx(); hb_sincos<true>(cx, x, s, c); return cx.oob ? 1 : 0; }
 extern "C" double rcp_fast(double d) { return hb_rcp(d); }
 template <int NN> static int spd(const double* A_packed, const double* b, double* x) {
   double A[NN * (NN + 1) / 2];
   for (int i = 0; i < NN * (NN + 1) / 2; i++) A[i] = A_packed[i];
-  int flag = 0;
-  hb_spd_solve<NN>(A, b, x, flag);
-  return flag;
+  int minpiv = 0x7fffffff;
+  hb_spd_solve<NN>(A, b, x, minpiv);
+  return minpiv < 0x00100000 ? HB_FLAG_NOT_SPD : 0;
 }
 extern "C" int spd_solve(int n, const double* A_packed, const double* b, double* x) {
   switch (n) {
