@@ -1,26 +1,35 @@
 #!/usr/bin/env python
-"""bench.py — BASELINE.json's metric on its configuration: phase-space RK4 steps/sec of the double pendulum
-(System 4 2), batch 1,048,576 random initial Phases per GPU, fp64 (configs[1]).
+"""bench.py — BASELINE.json's metric: phase-space RK4 steps/sec of batched trajectories, fp64.
 
 A bench "step" is ONE pass of the hot path over one batch: one `hb_batch_step(RK4, dt=0.01, nsteps=1)` call that reads
 every Phase of the batch from HBM, advances it by one classical RK4 step (4 hamEqs evaluations) and writes it back —
-the I/O-honest mode SURVEY.md §8(d) defines (32·n = 64 algorithmic bytes per trajectory-step), so `value` and
-`roofline` describe the same launches.  Batches rotate through a ring of buffers larger than L2 (see config.l2).
+the I/O-honest mode SURVEY.md §8(d) defines (32·n algorithmic bytes per trajectory-step), so `value` and `roofline`
+describe the same launches.  Batches rotate through a ring of buffers larger than L2 (see config.l2).
 
-  value     steps/s with the batch resident in HBM (device pointers through the C ABI), CUDA-event timed.
-  e2e       the same call through the C ABI with HOST buffers (pinned): H2D + kernel + D2H inside the timed region.
-  roofline  HBM roofline of the dominant kernel (hbk_double_pendulum_dflt_step_rk4) + the FP64-pipe view that actually binds.
-  cpu_baseline  the CPU oracle (restatement of the reference algorithm) timed on this box's host cores, bounded sample.
+Headline workload (N = 1 and the per-GPU shard at N > 1): BASELINE configs[1] — double pendulum (System 4 2), batch
+1,048,576 random initial Phases per GPU.  The K launches are captured into one CUDA graph; the graph is replayed R times so
+that the timed region is at least 100 ms (ms_per_step = region / (K·R)).
 
+  value      steps/s with the batch resident in HBM (device pointers through the C ABI), CUDA-event timed, max over ranks.
+  e2e        the same call through the C ABI with HOST buffers (pinned): H2D + kernel + D2H inside the timed region;
+             e2e.by_nsteps repeats it with 16 and 100 RK4 steps per call (what an evolveHam-style caller does).
+  roofline   HBM roofline of the dominant kernel (hbk_double_pendulum_dflt_step_rk4) + the instruction-issue view that binds it.
+  cpu_baseline   the CPU oracle (restatement of the reference algorithm) on this box's host cores, the SAME 1,048,576 batch.
+  configs    BASELINE configs[2], [3], [4] measured the same way (`--config 3|4|5` makes one of them the whole run):
+             "3" 2,097,152 pendulums (System 2 1) + 2,097,152 two-body orbits (System 4 2) on two streams,
+             "4" triple pendulum (System 6 3), 8,388,608 initial conditions split over the N GPUs (STRONG scaling), 1000 steps,
+                 one NCCL all-gather of the final Phases INSIDE the timed region,
+             "5" 12-link chain (System 24 12), batch 262,144.
 `--impl reference` times the reference's CPU implementation of the path: the Haskell+GSL binary cannot be built in this
-image (no GHC/GSL), so it is the oracle port (oracle/hamilton_oracle.c) on all host threads.
+image (no GHC/GSL), so it is the oracle port (oracle/hamilton_oracle.c) on all host threads, on the full batch.
 
-N > 1 (torchrun, one rank per GPU): trajectories are independent, so each rank owns its own 1,048,576-trajectory shard
-(weak scaling, no data-path collective); the single NCCL all-gather that collects the final Phases is executed after the
-timed steps and reported separately (gather_ms, value_with_gather).
+N > 1 (torchrun, one rank per GPU): trajectories are independent, so for `value` each rank owns its own 1,048,576-trajectory
+shard (weak scaling, no data-path collective; the all-gather of the final Phases is timed separately: gather_ms,
+value_with_gather); configs["4"] is the strong-scaling ensemble with the gather inside.
 """
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -34,14 +43,20 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
+PI = float(np.pi)
 N_PER_GPU = 1 << 20
 DT = 0.01
 SEED = 0x48414D49
-LO = [-np.pi, -np.pi, -1.0, -1.0]
-HI = [np.pi, np.pi, 1.0, 1.0]
-ALGO_BYTES_PER_STEP = 64          # 32·n, n = 2
-RING = 9                          # (in,out) buffer pairs: 9 × 64 MiB = 576 MiB touched per cycle >> 126 MB L2
 METRIC = "phase-space RK4 steps/sec (batched trajectories)"
+MIN_REGION_MS = 100.0
+# name -> (builtin id, n, lo, hi): sampling boxes of SURVEY.md §8(d)
+SYS = {
+    "pendulum": (0, 1, [-PI, -1.0], [PI, 1.0]),
+    "double_pendulum": (1, 2, [-PI, -PI, -1.0, -1.0], [PI, PI, 1.0, 1.0]),
+    "two_body": (3, 2, [1.0, -PI, -1.0, 1.0], [3.0, PI, 1.0, 5.0]),
+    "triple_pendulum": (6, 3, [-PI] * 3 + [-1.0] * 3, [PI] * 3 + [1.0] * 3),
+    "chain12": (7, 12, [-PI] * 12 + [-1.0] * 12, [PI] * 12 + [1.0] * 12),
+}
 
 
 def peaks():
@@ -54,8 +69,8 @@ def peaks():
 
 
 class ClockSampler:
-    """SM clock and throttle reasons DURING the timed region.  The region is tens of milliseconds long, so NVML is polled
-    from a thread every ~1 ms (nvidia-smi -lms cannot sample that fast); falls back to nvidia-smi when NVML is missing."""
+    """SM clock and throttle reasons DURING the timed region: NVML polled from a thread every ~1 ms, started well before the
+    region (falls back to `nvidia-smi -lms 20`)."""
 
     REASONS = (("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40), ("sw_power_cap", 0x4))
 
@@ -153,43 +168,224 @@ def bind_near_gpu(index):
 
 
 def cpu_oracle_steps_per_sec(target_seconds, threads):
-    """Times the oracle's RK4 on a bounded sample of the same workload (same RNG stream, first trajectories)."""
+    """Times the oracle's RK4 on the SAME 1,048,576-trajectory batch (same RNG stream); as many whole-batch steps as fit
+    the time target."""
     from oracle import oracle as O
     S = O.OracleSystem.builtin(O.DOUBLE_PENDULUM)
-    n_s = 16384 * max(1, threads)
-    y = S.init_random(SEED, 0, n_s, LO, HI)
-    t = time.perf_counter(); S.batch_step(y, 0, DT, 1, threads=threads); cal = time.perf_counter() - t
-    reps = max(1, min(64, int(target_seconds / max(cal, 1e-3))))
+    _id, _n, lo, hi = SYS["double_pendulum"]
+    y = S.init_random(SEED, 0, N_PER_GPU, lo, hi)
+    t = time.perf_counter(); y, _ = S.batch_step(y, 0, DT, 1, threads=threads); cal = time.perf_counter() - t
+    reps = max(1, min(200, int(target_seconds / max(cal, 1e-3))))
     t = time.perf_counter(); _, bad = S.batch_step(y, 0, DT, reps, threads=threads); el = time.perf_counter() - t
-    return n_s * reps / el, {"trajectories": n_s, "rk4_steps_each": reps, "seconds": round(el, 3), "failed": int(bad)}
+    return N_PER_GPU * reps / el, {"trajectories": N_PER_GPU, "rk4_steps_each": reps, "seconds": round(el, 3), "failed": int(bad)}
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU path (oracle port; Haskell+GSL unbuildable here), rank 0 only."""
+    """--impl reference: the reference's CPU path (oracle port; Haskell+GSL unbuildable here), rank 0 only, on the FULL
+    1,048,576-trajectory batch of the b200 arm's config."""
     if rank != 0:
         return
     from oracle import oracle as O
     threads = O.max_threads()
     S = O.OracleSystem.builtin(O.DOUBLE_PENDULUM)
-    n_s = 16384 * threads                       # bounded sample of the 1,048,576-trajectory batch
-    y = S.init_random(SEED, 0, n_s, LO, HI)
+    _id, _n, lo, hi = SYS["double_pendulum"]
+    y = S.init_random(SEED, 0, N_PER_GPU, lo, hi)
     for _ in range(args.warmup):
-        S.batch_step(y, 0, DT, 1, threads=threads)
+        y, _bad = S.batch_step(y, 0, DT, 1, threads=threads)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         y, _bad = S.batch_step(y, 0, DT, 1, threads=threads)
     el = time.perf_counter() - t0
-    v = n_s * args.steps / el
-    sample = "%d of the %d trajectories per step (same splitmix64 stream), %d RK4 steps, %d host threads" % (n_s, N_PER_GPU, args.steps, threads)
+    v = N_PER_GPU * args.steps / el
+    sample = "all %d trajectories of the batch per step (same splitmix64 stream), %d RK4 steps, %d host threads" % (N_PER_GPU, args.steps, threads)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "steps/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "double pendulum (System 4 2), batch 1,048,576 random Phases, RK4 dt=0.01 — CPU sample", "integrator": "rk4"},
+        "config": main_config(1, None),
         "cpu_baseline": {"value": v, "unit": "steps/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "oracle port of the reference algorithm (hamEqs via dense forward-mode jets + explicit inverse, classical RK4); "
                 "the ad+hmatrix+GSL Haskell binary cannot be built in this image (no GHC, no libgsl)"}))
+
+
+def main_config(world, extra):
+    c = {"workload": "double pendulum (System 4 2), batch 1,048,576 random initial Phases per GPU, RK4 dt=0.01, fp64 (BASELINE configs[1])",
+         "batch_per_gpu": N_PER_GPU, "global_batch": world * N_PER_GPU, "integrator": "rk4", "steps_per_launch": 1,
+         "layout": "AOS (array of Phases)", "parallelism": "%d independent shards" % world}
+    if extra:
+        c.update(extra)
+    return c
+
+
+class Harness:
+    """Device-resident timing of hb_batch_step(RK4, nsteps = 1) launches: K launches captured in one CUDA graph over a ring
+    of (in, out) buffer pairs larger than L2, replayed until the region is >= MIN_REGION_MS."""
+
+    def __init__(self, torch, hb, L, dev, rank, world, dist):
+        self.torch, self.hb, self.L, self.dev, self.rank, self.world, self.dist = torch, hb, L, dev, rank, world, dist
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def ring_for(self, name, N, first=0, min_bytes=576 << 20):
+        sid, n, lo, hi = SYS[name]
+        s = self.hb.systems.builtin(sid)
+        pair = 2 * N * 2 * n * 8
+        ring = max(3, min(12, int(math.ceil(min_bytes / pair))))
+        ins = [s.batch_init_random(SEED + r, first, N, lo, hi) for r in range(ring)]
+        outs = [self.torch.empty_like(b) for b in ins]
+        return s, ins, outs
+
+    def capture(self, launches, stream=None):
+        """launches: list of callables, each enqueues work on the current stream; returns a replay() callable."""
+        torch = self.torch
+        try:
+            g = torch.cuda.CUDAGraph()
+            cap = torch.cuda.Stream()
+            cap.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(cap):
+                with torch.cuda.graph(g, stream=cap):
+                    for f in launches:
+                        f()
+            torch.cuda.current_stream().wait_stream(cap)
+            return g.replay, "cuda_graph of K kernel launches"
+        except Exception as ex:   # pragma: no cover
+            sys.stderr.write("bench: CUDA-graph capture failed (%r); timing eager launches\n" % (ex,))
+            return (lambda: [f() for f in launches]), "eager"
+
+    def time_replays(self, replay, K, warm_replays=1, sampler=None):
+        """Returns (ms per launch, replays, clocks).  The region is exactly R replays of the K-launch graph."""
+        torch = self.torch
+        for _ in range(warm_replays):
+            replay()
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); replay(); e1.record()
+        self.barrier()
+        est = max(e0.elapsed_time(e1), 1e-3)
+        R = max(1, int(math.ceil(MIN_REGION_MS / est)))
+        if self.world > 1:   # every rank replays the same number of times
+            t = torch.tensor([R], dtype=torch.int64, device=self.dev)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            R = int(t.item())
+        self.barrier()
+        t0 = time.time()
+        e0.record()
+        for _ in range(R):
+            replay()
+        e1.record()
+        self.barrier()
+        t1 = time.time()
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop(t0, t1) if sampler is not None else None
+        return ms / (K * R), R, ms, clocks
+
+    def reduce_max(self, x):
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+
+def roofline_obj(n, N, launch_ms, kernel):
+    peak, peak_src = peaks()
+    algo = N * 32 * n
+    achieved = algo / (launch_ms * 1e-3) / 1e9
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "peak_source": peak_src, "kernel": kernel, "algorithmic_bytes_per_launch": algo}
+
+
+def bench_simple(H, name, N, K, kernel):
+    """One system, one batch, one step per launch."""
+    sid, n, lo, hi = SYS[name]
+    s, ins, outs = H.ring_for(name, N)
+    ring = len(ins)
+    L = H.L
+    for i in range(3):
+        s.batch_step(ins[i % ring], DT, 1, integ=L.RK4, out=outs[i % ring])
+    replay, how = H.capture([(lambda i=i: s.batch_step(ins[i % ring], DT, 1, integ=L.RK4, out=outs[i % ring])) for i in range(K)])
+    per, R, _ms, _ = H.time_replays(replay, K)
+    per = H.reduce_max(per)
+    return {"workload": "%s (System %d %d), batch %d, RK4 dt=0.01, one step per launch" % (name, 2 * n, n, N), "value": N / (per * 1e-3),
+            "unit": "steps/s", "ms_per_step": per, "launches_timed": K * R, "launch": how,
+            "l2": "ring of %d (in,out) pairs = %d MiB" % (ring, ring * 2 * N * 2 * n * 8 >> 20), "roofline": roofline_obj(n, N, per, kernel)}
+
+
+def bench_config3(H, K):
+    """2,097,152 pendulums (System 2 1) + 2,097,152 two-body orbits (System 4 2): two kernels on two streams per step."""
+    torch, L = H.torch, H.L
+    Np = 1 << 21
+    sp, pin, pout = H.ring_for("pendulum", Np, min_bytes=288 << 20)
+    st, tin, tout = H.ring_for("two_body", Np, min_bytes=288 << 20)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def step(i):
+        cur = torch.cuda.current_stream()
+        s1.wait_stream(cur); s2.wait_stream(cur)
+        with torch.cuda.stream(s1):
+            sp.batch_step(pin[i % len(pin)], DT, 1, integ=L.RK4, out=pout[i % len(pin)])
+        with torch.cuda.stream(s2):
+            st.batch_step(tin[i % len(tin)], DT, 1, integ=L.RK4, out=tout[i % len(tin)])
+        cur.wait_stream(s1); cur.wait_stream(s2)
+    for i in range(3):
+        step(i)
+    replay, how = H.capture([(lambda i=i: step(i)) for i in range(K)])
+    per, R, _ms, _ = H.time_replays(replay, K)
+    algo = Np * 32 + Np * 64
+    peak, peak_src = peaks()
+    ach = algo / (per * 1e-3) / 1e9
+    return {"workload": "2,097,152 pendulums (System 2 1) + 2,097,152 two-body orbits (System 4 2), mixed batch 4,194,304, two streams (BASELINE configs[2])",
+            "value": 2 * Np / (per * 1e-3), "unit": "steps/s", "ms_per_step": per, "launches_timed": 2 * K * R, "launch": how,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                         "kernel": "hbk_pendulum_step_rk4 + hbk_two_body_dflt_step_rk4 (concurrent)", "algorithmic_bytes_per_launch": algo}}
+
+
+def bench_config4(H, steps=1000):
+    """Triple pendulum, 8,388,608 initial conditions split over the ranks (strong scaling); `steps` one-step launches, then ONE
+    all-gather of the final Phases (NCCL over NVLink), all inside the timed region."""
+    torch, L, dist, world, rank = H.torch, H.L, H.dist, H.world, H.rank
+    total = 8 << 20
+    N = total // world
+    sid, n, lo, hi = SYS["triple_pendulum"]
+    s = H.hb.systems.builtin(sid)
+    a = s.batch_init_random(SEED, rank * N, N, lo, hi)
+    b = torch.empty_like(a)
+    allp = torch.empty((total, 2 * n), dtype=a.dtype, device=H.dev) if world > 1 else None
+    bufs = [a, b]
+    for i in range(4):
+        s.batch_step(bufs[i % 2], DT, 1, integ=L.RK4, out=bufs[(i + 1) % 2])
+    K = 100                                                  # the graph holds 100 launches; steps / 100 replays
+    replay, how = H.capture([(lambda i=i: s.batch_step(bufs[i % 2], DT, 1, integ=L.RK4, out=bufs[(i + 1) % 2])) for i in range(K)])
+    if world > 1:
+        for _ in range(2):                                   # warm the communicator and its buffer registration
+            dist.all_gather_into_tensor(allp, bufs[0])
+    replay()
+    H.barrier()
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    e0.record()
+    for _ in range(steps // K):
+        replay()
+    e1.record()
+    if world > 1:
+        dist.all_gather_into_tensor(allp, bufs[0])
+    e2.record()
+    H.barrier()
+    ms_steps, ms_all = H.reduce_max(e0.elapsed_time(e1)), H.reduce_max(e0.elapsed_time(e2))
+    done = (steps // K) * K
+    per = ms_steps / done
+    out = {"workload": "triple pendulum (System 6 3), 8,388,608 initial conditions over %d GPU(s), %d RK4 steps dt=0.01 (one per launch, state in HBM every step), all-gather of the final Phases inside the timed region (BASELINE configs[3])" % (world, done),
+           "scaling": "strong", "batch_per_gpu": N, "value": total * done / (ms_all * 1e-3), "unit": "steps/s", "ms_total": ms_all,
+           "ms_steps": ms_steps, "gather_ms": ms_all - ms_steps, "gather_bytes": total * 2 * n * 8 if world > 1 else 0,
+           "value_without_gather": total * done / (ms_steps * 1e-3), "ms_per_step": per, "launch": how,
+           "l2": "two buffers of %d MiB ping-pong (a real stepping loop); per-GPU state %s L2" % (N * 2 * n * 8 >> 20, "larger than" if 2 * N * 2 * n * 8 > (126 << 20) else "within"),
+           "roofline": roofline_obj(n, N, per, "hbk_triple_pendulum_dflt_step_rk4")}
+    if world > 1:
+        out["gather_bus_GBps"] = total * 2 * n * 8 * (world - 1) / world / ((ms_all - ms_steps) * 1e-3) / 1e9
+    return out
 
 
 def main():
@@ -199,7 +395,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
-    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of one CUDA graph of K launches")
+    ap.add_argument("--config", type=int, default=0, choices=[0, 2, 3, 4, 5], help="0/2: the headline line (+ the other configs as sub-objects); 3|4|5: only that BASELINE config")
+    ap.add_argument("--no-extras", action="store_true", help="skip configs 3-5 and the e2e sweep (quick runs)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -224,59 +421,40 @@ def main():
     numa = bind_near_gpu(local_rank)       # page-locked host buffers of the e2e leg land on the GPU's own NUMA node
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    H = Harness(torch, hb, L, dev, rank, world, dist)
+    K = args.steps
 
-    sysm = hb.systems.builtin(hb.systems.DOUBLE_PENDULUM)          # ahead-of-time sm_100a kernels, m1 = m2 = 1
-    N = N_PER_GPU
-    first = rank * N                                                # contiguous block split of the global ensemble
-    ring_in = [sysm.batch_init_random(SEED + r, first, N, LO, HI) for r in range(RING)]
-    ring_out = [torch.empty_like(b) for b in ring_in]
-    flags = torch.zeros(N, dtype=torch.int32, device=dev)
-
-    def barrier():
+    if args.config in (3, 4, 5):          # one secondary config as the whole run
+        if args.config == 3:
+            r = bench_config3(H, K)
+        elif args.config == 4:
+            r = bench_config4(H)
+        else:
+            r = bench_simple(H, "chain12", 1 << 18, K, "hbk_chain12_step_rk4")
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": r["value"], "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
+                              "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": r.get("scaling", "weak"), "vs_baseline": None,
+                              "dtype": "f64", "data": "synthetic", "config": {"workload": r["workload"]}, "roofline": r["roofline"], "detail": r}))
         if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+            dist.destroy_process_group()
+        return
+
+    # ---------------- headline: device-resident throughput (value, roofline) ----------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()                                                 # polling starts seconds before the timed region
+    sysm, ring_in, ring_out = H.ring_for("double_pendulum", N_PER_GPU, first=rank * N_PER_GPU)
+    RING = len(ring_in)
+    N = N_PER_GPU
+    flags = torch.zeros(N, dtype=torch.int32, device=dev)
 
     def step(i):
         sysm.batch_step(ring_in[i % RING], DT, 1, integ=L.RK4, out=ring_out[i % RING], flags=flags)
 
-    # ---------------- device-resident throughput (value, roofline) ----------------
     for i in range(args.warmup):
         step(i)
-    barrier()
-    # The K timed launches are captured once into a CUDA graph (the C ABI is stream-ordered and capture-safe), so the
-    # timed region holds exactly K kernel launches and no per-call host overhead; falls back to eager launches.
-    graph = None
-    if not args.no_graph:
-        try:
-            graph = torch.cuda.CUDAGraph()
-            cap = torch.cuda.Stream()
-            cap.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(cap):
-                with torch.cuda.graph(graph, stream=cap):
-                    for i in range(args.steps):
-                        step(i)
-            torch.cuda.current_stream().wait_stream(cap)
-        except Exception as ex:   # pragma: no cover
-            sys.stderr.write("bench: CUDA-graph capture failed (%r); timing eager launches\n" % (ex,))
-            graph = None
-    barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    t0 = time.time()
-    e0.record()
-    if graph is not None:
-        graph.replay()
-    else:
-        for i in range(args.steps):
-            step(i)
-    e1.record()
-    barrier()
-    t1 = time.time()
-    ms = e0.elapsed_time(e1)
-    clocks = sampler.stop(t0, t1)
+    H.barrier()
+    replay, how = H.capture([(lambda i=i: step(i)) for i in range(K)])
+    launch_ms, R, region_ms, clocks = H.time_replays(replay, K, sampler=sampler)
     assert int(flags.sum().item()) == 0, "numerical failure flags raised during the bench"
 
     # explanation only: the same kernel with 16 RK4 steps fused per launch (state stays in registers between steps)
@@ -288,63 +466,95 @@ def main():
     f1.record()
     torch.cuda.synchronize()
     fused_value = world * N * 16 * 8 / (f0.elapsed_time(f1) * 1e-3)
+    # explanation only: a real stepping loop (each launch reads what the previous one wrote: L2-resident 32 MiB state)
+    ca, cb = ring_in[0].clone(), ring_out[0]
+    chain, _ = H.capture([(lambda i=i: sysm.batch_step(ca if i % 2 == 0 else cb, DT, 1, integ=L.RK4, out=cb if i % 2 == 0 else ca)) for i in range(K)])
+    chain_ms, _, _, _ = H.time_replays(chain, K)
 
     # ---------------- final collection: one NCCL all-gather of the final Phases ----------------
     gather_ms = 0.0
     if world > 1:
-        final = ring_out[(args.steps - 1) % RING]
+        final = ring_out[(K - 1) % RING]
         allp = torch.empty((world * N, final.shape[1]), dtype=final.dtype, device=dev)
-        dist.all_gather_into_tensor(allp, final)                  # warm the communicator
-        barrier()
+        for _ in range(2):
+            dist.all_gather_into_tensor(allp, final)                  # warm the communicator
+        H.barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record(); dist.all_gather_into_tensor(allp, final); g1.record()
-        barrier()
+        H.barrier()
         gather_ms = g0.elapsed_time(g1)
+        del allp
 
     # ---------------- end to end through the C ABI with host buffers ----------------
     h_in = [torch.empty((N, 4), dtype=torch.float64).pin_memory() for _ in range(2)]
     h_out = [torch.empty((N, 4), dtype=torch.float64).pin_memory() for _ in range(2)]
     for b, src in zip(h_in, ring_in):
         b.copy_(src.cpu())
-    e2e_steps = max(3, min(args.steps, 50))
-    for i in range(3):
-        sysm.batch_step(h_in[i % 2], DT, 1, integ=L.RK4, out=h_out[i % 2])
-    barrier()
-    w0 = time.perf_counter()
-    for i in range(e2e_steps):
-        sysm.batch_step(h_in[i % 2], DT, 1, integ=L.RK4, out=h_out[i % 2])   # blocking: returns when the result is on the host
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - w0
-    chk = float(h_out[0][0, 0])                                    # result is read on the host
-    assert np.isfinite(chk)
+
+    def e2e(nsteps, calls):
+        for i in range(3):
+            sysm.batch_step(h_in[i % 2], DT, nsteps, integ=L.RK4, out=h_out[i % 2])
+        H.barrier()
+        w0 = time.perf_counter()
+        for i in range(calls):
+            sysm.batch_step(h_in[i % 2], DT, nsteps, integ=L.RK4, out=h_out[i % 2])   # blocking: returns when the result is on the host
+        torch.cuda.synchronize()
+        el = time.perf_counter() - w0
+        assert np.isfinite(float(h_out[0][0, 0]))                 # result is read on the host
+        return H.reduce_max(el * 1e3), calls
+    e2e_calls = max(3, min(K, 50))
+    e2e_ms, _ = e2e(1, e2e_calls)
+    by_nsteps = {}
+    if not args.no_extras:
+        for ns in (16, 100):
+            ms_ns, calls = e2e(ns, 20)
+            by_nsteps[str(ns)] = {"value": world * N * ns * calls / (ms_ns * 1e-3), "unit": "steps/s", "rk4_steps_per_call": ns, "calls": calls,
+                                  "h2d_bytes_per_call": N * 32, "d2h_bytes_per_call": N * 32}
+    del h_in, h_out
+
+    # ---------------- the other BASELINE configs ----------------
+    configs = {}
+    if not args.no_extras:
+        del ring_in, ring_out
+        torch.cuda.empty_cache()
+        try:
+            configs["4"] = bench_config4(H)
+            if world == 1:
+                configs["3"] = bench_config3(H, min(K, 200))
+                configs["5"] = bench_simple(H, "chain12", 1 << 18, min(K, 100), "hbk_chain12_step_rk4")
+        except Exception as ex:   # pragma: no cover
+            configs["error"] = repr(ex)
 
     # ---------------- reduce over ranks (max time) ----------------
-    times = torch.tensor([ms, gather_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    times = torch.tensor([launch_ms, gather_ms, chain_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms, gather_ms, e2e_ms = [float(x) for x in times.tolist()]
+    launch_ms, gather_ms, chain_ms = [float(x) for x in times.tolist()]
 
     if rank == 0:
-        total_steps = world * N * args.steps
-        value = total_steps / (ms * 1e-3)
-        launch_ms = ms / args.steps
-        peak, peak_src = peaks()
-        achieved = N * ALGO_BYTES_PER_STEP / (launch_ms * 1e-3) / 1e9
-        traffic = None
-        fp64 = None
+        total_steps = world * N * K * R
+        value = world * N / (launch_ms * 1e-3)
+        roof = roofline_obj(2, N, launch_ms, "hbk_double_pendulum_dflt_step_rk4")
         try:
-            with open(os.path.join(ROOT, "profiles", "roofline_r1.json")) as f:
+            with open(os.path.join(ROOT, "profiles", "roofline_r2.json")) as f:
                 prof = json.load(f)
-            traffic = prof.get("dram_bytes_per_launch")
-            fp64 = prof.get("fp64")
-            # live FP64 view: issue cycles the step needs on the FP64 pipe (static SASS count, 3-operand DFMAs at 3 clocks)
-            # against the cycles the schedulers had — the resource that actually binds this kernel
-            cyc = fp64.get("fp64_issue_cycles_per_rk4_step") if fp64 else None
+            roof["traffic"] = prof.get("dram_bytes_per_launch")
+            issue = prof.get("issue")
+            # live issue view: issue clocks one trajectory-step needs (static SASS count under the measured issue model: FP64
+            # instruction 2 clocks, 3 with three distinct register operands, any other instruction 1) against the clocks the
+            # schedulers had — the resource that binds this kernel
+            cyc = issue.get("issue_clocks_per_trajectory_step") if issue else None
             mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz")
             if cyc and mhz:
                 sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
-                bound = sms * 4 * 32 * mhz * 1e6 / cyc                # steps/s per GPU at 100 % FP64 issue
-                fp64 = dict(fp64, fp64_bound_steps_per_s_at_measured_clock=bound, achieved_frac_of_fp64_bound=value / world / bound)
+                bound = sms * 4 * 32 * mhz * 1e6 / cyc
+                issue = dict(issue, issue_bound_steps_per_s_at_measured_clock=bound, achieved_frac_of_issue_bound=value / world / bound)
+                f64 = issue.get("fp64_issue_clocks_per_trajectory_step")
+                if f64:
+                    b64 = sms * 4 * 32 * mhz * 1e6 / f64
+                    issue = dict(issue, fp64_bound_steps_per_s_at_measured_clock=b64, achieved_frac_of_fp64_bound=value / world / b64)
+            roof["issue"] = issue
+            roof["note"] = "the binding resource is instruction issue on the FP64-heavy stream, not HBM (SURVEY.md §8(d), DESIGN.md §4); see issue"
         except Exception:
             pass
         cpu_v = cpu_sample = cpu_threads = None
@@ -354,31 +564,28 @@ def main():
             cpu_threads = O.max_threads()
             cpu_v, cpu_sample = cpu_oracle_steps_per_sec(args.cpu_seconds, cpu_threads)
         out = {
-            "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
             "ms_per_step": launch_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": "double pendulum (System 4 2), batch 1,048,576 random initial Phases per GPU, RK4 dt=0.01, fp64 (BASELINE configs[1])",
-                       "batch_per_gpu": N, "global_batch": world * N, "integrator": "rk4", "steps_per_launch": 1, "layout": "AOS (array of Phases)",
-                       "launch": "cuda_graph of K kernel launches" if graph is not None else "eager",
-                       "parallelism": "%d independent shards" % world,
-                       "l2": "inputs larger than L2: ring of %d (in,out) batch pairs = %d MiB touched per cycle" % (RING, RING * 64)},
+            "config": main_config(world, {"launch": how, "graph_replays": R, "timed_region_ms": region_ms, "launches_timed": K * R,
+                                          "l2": "inputs larger than L2: ring of %d (in,out) batch pairs = %d MiB touched per cycle" % (RING, RING * 64)}),
             "clocks": clocks,
-            "gpu_launches": args.steps,
-            "e2e": {"value": world * N * e2e_steps / (e2e_ms * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": N * 32, "d2h_bytes_per_step": N * 32,
-                    "steps": e2e_steps, "call": "hb_batch_step(HB_INTEG_RK4, nsteps=1, HB_MEM_HOST) on pinned host arrays, blocking: one kernel reads the Phases from and writes the results to host memory over PCIe (DESIGN.md section 2)",
-                    "host_binding": numa},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "peak_source": peak_src, "kernel": "hbk_double_pendulum_dflt_step_rk4",
-                         "algorithmic_bytes_per_launch": N * ALGO_BYTES_PER_STEP,
-                         "note": "the binding resource is the FP64 pipe, not HBM (SURVEY.md §8(d)); see fp64", "fp64": fp64},
+            "gpu_launches": K * R,
+            "e2e": {"value": world * N * e2e_calls / (e2e_ms * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": N * 32, "d2h_bytes_per_step": N * 32,
+                    "steps": e2e_calls, "call": "hb_batch_step(HB_INTEG_RK4, nsteps=1, HB_MEM_HOST) on pinned host arrays, blocking: one kernel reads the Phases from and writes the results to host memory over PCIe (DESIGN.md section 2)",
+                    "host_binding": numa, "by_nsteps": by_nsteps},
+            "roofline": roof,
+            "fused16": {"value": fused_value, "unit": "steps/s", "note": "16 RK4 steps per launch, no per-step HBM traffic (issue-bound view)"},
+            "chain": {"value": world * N / (chain_ms * 1e-3), "unit": "steps/s", "ms_per_step": chain_ms,
+                      "note": "explanation only: K dependent one-step launches ping-ponging between two buffers (32 MiB state stays in L2)"},
+            "configs": configs,
         }
-        out["fused16"] = {"value": fused_value, "unit": "steps/s", "note": "16 RK4 steps per launch, no per-step HBM traffic (FP64-pipe view)"}
         if world > 1:
             out["gather_ms"] = gather_ms
-            out["value_with_gather"] = total_steps / ((ms + gather_ms) * 1e-3)
+            out["value_with_gather"] = total_steps / ((launch_ms * K * R + gather_ms) * 1e-3)
         if cpu_v is not None:
             out["cpu_baseline"] = {"value": cpu_v, "unit": "steps/s", "cores": cpu_threads, "kind": "port",
-                                   "sample": "%(trajectories)d trajectories x %(rk4_steps_each)d RK4 steps in %(seconds)s s (oracle/hamilton_oracle.c, pthreads)" % cpu_sample}
+                                   "sample": "all %(trajectories)d trajectories x %(rk4_steps_each)d RK4 steps in %(seconds)s s (oracle/hamilton_oracle.c, pthreads)" % cpu_sample}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -4,7 +4,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libhamilton_b200.so")
+# HB_LIB_PATH: development knob (A/B of a saved build of this same library on one GPU box, profiles/exp/exp_r2_ab.py)
+LIB_PATH = os.environ.get("HB_LIB_PATH") or os.path.join(_HERE, "lib", "libhamilton_b200.so")
 
 # hb_status
 OK, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_COMPILE, ERR_TAPE, ERR_NUMERIC, ERR_UNSUPPORTED = range(8)

@@ -44,6 +44,13 @@
 // column per thread (conflict-free), so that the registers are left to the mass matrix and its factor.
 #define HB_BIG_N 8
 #define HB_DYN_DOUBLES(NCOORD, NE_) ((NCOORD) >= HB_BIG_N ? 3 * 2 * (NCOORD) + (NE_) : 0)
+// Dynamic shared memory of every kernel (hb_dsm), in this order — csrc/runtime.cpp dyn_smem_bytes() computes the same sizes:
+//   small systems (n < HB_BIG_N):  [ sin/cos table image: HB_TAB_BYTES ]  [ stage: 2 x DIN doubles per thread, the cp.async
+//                                  landing zone of the thread's next Phase ]  [ xp ]
+//   large systems:                 [ RK vectors + parked values: HB_DYN_DOUBLES per thread ]  [ xp ]
+//   xp = DOUT doubles per thread, the warps' transpose buffers for host-memory stores; present only when a.layout == 2
+//   and DOUT is even and <= HB_WSTORE_MAXD.
+#define HB_TAB_BYTES 32896   // sizeof(HbTab) rounded up to 128 (static_assert below)
 // Upper bound of the CTA size a kernel may be launched with (= __launch_bounds__).  A sweep of CTA sizes 128..384 x
 // resident waves 1..4 on B200 (profiles/r1d/sweep.txt) was flat within run-to-run noise, so it is the default size.
 #define HB_MAXBLOCK_OF(NCOORD) HB_BLOCK_OF(NCOORD)
@@ -103,13 +110,13 @@ HB_DEV void hb_load(const double* __restrict__ base, I i, I N, int layout, doubl
 // contiguous bytes.  A thread-per-Phase store (16 bytes at a 2n*8-byte stride) reaches the host as partial-sector
 // writes: 12.7 GB/s measured against 53.6 GB/s for the transposed form (profiles/r1h/zc.txt).
 template <int D, class I>
-HB_DEV void hb_store(double* __restrict__ base, I i, I N, int layout, const double (&y)[D]) {
+HB_DEV void hb_store(double* __restrict__ base, I i, I N, int layout, const double (&y)[D], double* xp = nullptr) {
   if constexpr (D % 2 == 0 && D <= HB_WSTORE_MAXD) {
     if (layout == 2) {
-      if (__activemask() == 0xffffffffu) {   // whole warp here together: lanes hold 32 consecutive trajectories
-        __shared__ double2 xp[HB_MAXBLOCK_OF(D / 2) * (D / 2)];
+      // xp: this warp's transpose buffer (32 * D doubles of the kernel's dynamic shared memory; null on the slow path)
+      if (xp != nullptr && __activemask() == 0xffffffffu) {   // whole warp here together: lanes hold 32 consecutive trajectories
         const int lane = threadIdx.x & 31;
-        double2* w = xp + (threadIdx.x - lane) * (D / 2);
+        double2* w = reinterpret_cast<double2*>(xp);
 #pragma unroll
         for (int c = 0; c < D / 2; c++) w[lane * (D / 2) + c] = make_double2(y[2 * c], y[2 * c + 1]);
         __syncwarp();
@@ -142,6 +149,7 @@ HB_DEV void hb_store(double* __restrict__ base, I i, I N, int layout, const doub
 #ifndef HB_PRE_L2
 #define HB_PRE_L2 1
 #endif
+
 template <int D, class I>
 HB_DEV void hb_prefetch_l2(const double* base, I i, I N, int layout) {
 #ifdef HB_HOST_EMU
@@ -156,17 +164,6 @@ HB_DEV void hb_prefetch_l2(const double* base, I i, I N, int layout) {
   }
 #endif
 }
-HB_DEV bool hb_finite(double x) { return (__double2hiint(x) & 0x7ff00000) != 0x7ff00000; }
-// HB_HOST_EMU: tests/host_engine_harness.cpp compiles this header as HOST code (one "thread", CUDA built-ins stubbed) so
-// that hamEqs, the SPD solves, RK4, the GSL-RKF45 stepper/controller and the fast sincos/reciprocal can be checked
-// against the oracle without a GPU.  Only the inline-PTX sites need an alternative; device builds never define it.
-#ifdef HB_HOST_EMU
-#define HB_PDL_LAUNCH_DEPENDENTS() ((void)0)
-#define HB_PDL_WAIT() ((void)0)
-#else
-#define HB_PDL_LAUNCH_DEPENDENTS() asm volatile("griddepcontrol.launch_dependents;")
-#define HB_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
-#endif
 // Shared-window address of a shared-memory object, computed ONCE: the volatile asm keeps ptxas from rematerialising the
 // generic->shared conversion (S2R SR_CgaCtaId + MOV + LEA) in front of every use inside the trajectory loop.
 HB_DEV unsigned hb_smem_addr(const void* p) {
@@ -178,12 +175,58 @@ HB_DEV unsigned hb_smem_addr(const void* p) {
   return r;
 #endif
 }
+// cp.async (LDGSTS) staging of one array-of-records trajectory: D/2 16-byte copies straight into shared memory, no
+// destination registers — so the copy of the NEXT Phase can be issued a whole trajectory ahead.  (A register prefetch is
+// sunk by ptxas to the end of the current step to shorten its live range, and the DRAM latency it should hide comes back
+// as a long-scoreboard stall on the first use: 35 % of all warp samples, profiles/r2a.)  Slot layout: double2 c of thread t
+// at slot[(c * blockDim + t)]: conflict-free LDS.128.
+// slot: this thread's first double2 of the stage buffer (generic pointer, used by the host emulation);  slot_s: its
+// shared-window address;  cstride: bytes between the thread's consecutive double2 (= 16 * blockDim)
+template <int D>
+HB_DEV void hb_async_load(double* slot, unsigned slot_s, unsigned cstride, const double* src) {
+#ifdef HB_HOST_EMU
+  (void)slot_s;
+#pragma unroll
+  for (int c = 0; c < D / 2; c++) { slot[c * (cstride / 8)] = src[2 * c]; slot[c * (cstride / 8) + 1] = src[2 * c + 1]; }
+#else
+  (void)slot;
+#pragma unroll
+  for (int c = 0; c < D / 2; c++)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(slot_s + c * cstride), "l"(src + 2 * c) : "memory");
+  asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int D>
+HB_DEV void hb_async_read(const double* slot, unsigned slot_s, unsigned cstride, double (&y)[D]) {
+#ifdef HB_HOST_EMU
+  (void)slot_s;
+#pragma unroll
+  for (int c = 0; c < D / 2; c++) { y[2 * c] = slot[c * (cstride / 8)]; y[2 * c + 1] = slot[c * (cstride / 8) + 1]; }
+#else
+  (void)slot;
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+  for (int c = 0; c < D / 2; c++)
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(y[2 * c]), "=d"(y[2 * c + 1]) : "r"(slot_s + c * cstride) : "memory");
+#endif
+}
+HB_DEV bool hb_finite(double x) { return (__double2hiint(x) & 0x7ff00000) != 0x7ff00000; }
+// HB_HOST_EMU: tests/host_engine_harness.cpp compiles this header as HOST code (one "thread", CUDA built-ins stubbed) so
+// that hamEqs, the SPD solves, RK4, the GSL-RKF45 stepper/controller and the fast sincos/reciprocal can be checked
+// against the oracle without a GPU.  Only the inline-PTX sites need an alternative; device builds never define it.
+#ifdef HB_HOST_EMU
+#define HB_PDL_LAUNCH_DEPENDENTS() ((void)0)
+#define HB_PDL_WAIT() ((void)0)
+#else
+#define HB_PDL_LAUNCH_DEPENDENTS() asm volatile("griddepcontrol.launch_dependents;")
+#define HB_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+#endif
 #ifdef HB_HOST_EMU
 static double hb_dsm[1 << 17];
 HB_DEV double hb_lds(const double* p) { return *p; }
 HB_DEV void hb_sts(double* p, double v) { *p = v; }
 #else
-extern __shared__ __align__(16) double hb_dsm[];   // dynamic shared memory (large systems only)
+extern __shared__ __align__(128) double hb_dsm[];   // dynamic shared memory (layout: HB_DYN_DOUBLES above)
 HB_DEV double hb_lds(const double* p) {   // opaque to the optimiser: a parked value is re-read, never kept in a register
   double v;
   asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
@@ -222,6 +265,7 @@ struct HbCtx {
   unsigned tab_s;       // shared-window address of the staged sin/cos table (fast path only)
   unsigned oob;         // non-zero when a fast-path primitive saw an argument outside its domain
   int minpiv;           // smallest high word of any mass-matrix pivot seen (hb_bad_pivot test deferred to the end)
+  double* xp;           // this warp's transpose buffer for host-memory stores (layout 2), else null
 };
 HB_DEV void hb_ctx_reset(HbCtx& cx) { cx.oob = 0; cx.minpiv = 0x7fffffff; }
 
@@ -258,6 +302,7 @@ struct HbTab {
   double2 e[HB_SC_N];
   unsigned long long bar;
 };
+static_assert(sizeof(HbTab) <= HB_TAB_BYTES, "HB_TAB_BYTES must hold the table image");
 #ifndef HB_TAB_BULK
 #define HB_TAB_BULK (HB_SC_LOG2 == HB_SC_TAB_LOG2)   // whole table: ONE cp.async.bulk (TMA, UBLKCP) per CTA instead of a load/store loop
 #endif
@@ -716,6 +761,8 @@ struct HbRkf45 {
 };
 
 // One rkf45_apply: y <- y + h * (5th-order increment); yerr; dydt_out = F(y_new).  k1 = dydt_in.
+// Every product and sum is written as an explicit fma / multiply: no expression is left for the compiler to contract one
+// way or another, so all instances of this code (layout-specialised, ahead-of-time, NVRTC) give bit-identical results.
 template <class S, bool FAST>
 HB_DEV void hb_rkf45_apply(HbCtx& cx, const double* prm, const double* w, double h, double (&y)[2 * S::N],
                            const double (&k1)[2 * S::N], double (&yerr)[2 * S::N],
@@ -723,27 +770,28 @@ HB_DEV void hb_rkf45_apply(HbCtx& cx, const double* prm, const double* w, double
   constexpr int D = 2 * S::N;
   typedef HbRkf45 T;
   double k2[D], k3[D], k4[D], k5[D], k6[D], yt[D];
+  const double h4 = T::ah0 * h;
 #pragma unroll
-  for (int c = 0; c < D; c++) yt[c] = y[c] + T::ah0 * h * k1[c];
+  for (int c = 0; c < D; c++) yt[c] = fma(h4, k1[c], y[c]);
   hb_rhs<S, FAST>(cx, prm, w, yt, k2, flag);
 #pragma unroll
-  for (int c = 0; c < D; c++) yt[c] = y[c] + h * (T::b30 * k1[c] + T::b31 * k2[c]);
+  for (int c = 0; c < D; c++) yt[c] = fma(h, fma(T::b30, k1[c], T::b31 * k2[c]), y[c]);
   hb_rhs<S, FAST>(cx, prm, w, yt, k3, flag);
 #pragma unroll
-  for (int c = 0; c < D; c++) yt[c] = y[c] + h * (T::b40 * k1[c] + T::b41 * k2[c] + T::b42 * k3[c]);
+  for (int c = 0; c < D; c++) yt[c] = fma(h, fma(T::b40, k1[c], fma(T::b41, k2[c], T::b42 * k3[c])), y[c]);
   hb_rhs<S, FAST>(cx, prm, w, yt, k4, flag);
 #pragma unroll
-  for (int c = 0; c < D; c++) yt[c] = y[c] + h * (T::b50 * k1[c] + T::b51 * k2[c] + T::b52 * k3[c] + T::b53 * k4[c]);
+  for (int c = 0; c < D; c++) yt[c] = fma(h, fma(T::b50, k1[c], fma(T::b51, k2[c], fma(T::b52, k3[c], T::b53 * k4[c]))), y[c]);
   hb_rhs<S, FAST>(cx, prm, w, yt, k5, flag);
 #pragma unroll
   for (int c = 0; c < D; c++)
-    yt[c] = y[c] + h * (T::b60 * k1[c] + T::b61 * k2[c] + T::b62 * k3[c] + T::b63 * k4[c] + T::b64 * k5[c]);
+    yt[c] = fma(h, fma(T::b60, k1[c], fma(T::b61, k2[c], fma(T::b62, k3[c], fma(T::b63, k4[c], T::b64 * k5[c])))), y[c]);
   hb_rhs<S, FAST>(cx, prm, w, yt, k6, flag);
 #pragma unroll
   for (int c = 0; c < D; c++) {
-    const double di = T::c1 * k1[c] + T::c3 * k3[c] + T::c4 * k4[c] + T::c5 * k5[c] + T::c6 * k6[c];
-    y[c] += h * di;
-    yerr[c] = h * (T::e1 * k1[c] + T::e3 * k3[c] + T::e4 * k4[c] + T::e5 * k5[c] + T::e6 * k6[c]);
+    const double di = fma(T::c1, k1[c], fma(T::c3, k3[c], fma(T::c4, k4[c], fma(T::c5, k5[c], T::c6 * k6[c]))));
+    y[c] = fma(h, di, y[c]);
+    yerr[c] = h * fma(T::e1, k1[c], fma(T::e3, k3[c], fma(T::e4, k4[c], fma(T::e5, k5[c], T::e6 * k6[c]))));
   }
   hb_rhs<S, FAST>(cx, prm, w, y, dydt_out, flag);
 }
@@ -790,7 +838,7 @@ HB_DEV void hb_rkf45_to(HbCtx& cx, const double* prm, const double* w, double (&
       bool tiny = true;
 #pragma unroll
       for (int c = 0; c < D; c++) {
-        const double D0 = T::eps * (fabs(y[c]) + fabs(h_old * dout[c])) + T::eps;
+        const double D0 = fma(T::eps, fabs(y[c]) + fabs(h_old * dout[c]), T::eps);
         tiny = tiny && (fabs(yerr[c]) <= 3.3e-5 * D0);
       }
 #ifndef HB_NO_RKF45_SHORTCUT
@@ -799,7 +847,7 @@ HB_DEV void hb_rkf45_to(HbCtx& cx, const double* prm, const double* w, double (&
       double rmax = 2.2250738585072014e-308;   // DBL_MIN
 #pragma unroll
       for (int c = 0; c < D; c++) {
-        const double D0 = T::eps * (fabs(y[c]) + fabs(h_old * dout[c])) + T::eps;
+        const double D0 = fma(T::eps, fabs(y[c]) + fabs(h_old * dout[c]), T::eps);
         const double r = fabs(yerr[c]) / fabs(D0);
         rmax = r > rmax ? r : rmax;
       }
@@ -843,8 +891,8 @@ HB_DEV void hb_rkf45_to(HbCtx& cx, const double* prm, const double* w, double (&
 #ifndef HB_LAYSPEC
 #define HB_LAYSPEC 1
 #endif
-#ifndef HB_PINGPONG
-#define HB_PINGPONG 1      // small records: two Phase buffers swap roles in a 2x unrolled loop (no register copy of the prefetched Phase)
+#ifndef HB_ASYNC_STAGE
+#define HB_ASYNC_STAGE 1   // small systems, array of records: the next Phase is staged by cp.async into shared memory (0: plain loads)
 #endif
 template <int LAY> HB_DEV int hb_lay_of(const HbKArgs& a) { if constexpr (LAY < 0) return a.layout; else return LAY; }
 // HB_FLAG_* bits of one trajectory: what the integrators raised + the deferred pivot test
@@ -883,7 +931,7 @@ HB_DEV void hb_traj_step_rk4(const HbKArgs& a, I i, const double* yin, const dou
     else for (int s = 0; s < a.nsteps; s++) hb_rk4_step<S, FAST>(cx, a.prm, w, y, a.dt, a.dt6, a.dth, flag);
   }
   if (FAST && cx.oob) return;
-  hb_store<D, I>(a.out, i, (I)a.N, hb_lay_of<LAY>(a), y);
+  hb_store<D, I>(a.out, i, (I)a.N, hb_lay_of<LAY>(a), y, cx.xp);
   hb_finish<D, I>(a, i, y, cx, flag);
 }
 // stepHam iterated with reference semantics: each step is a fresh adaptive solve over (0, dt)
@@ -903,7 +951,7 @@ HB_DEV void hb_traj_step_rkf45(const HbKArgs& a, I i, const double* yin, const d
     }
   }
   if (FAST && cx.oob) return;
-  hb_store<D, I>(a.out, i, (I)a.N, hb_lay_of<LAY>(a), y);
+  hb_store<D, I>(a.out, i, (I)a.N, hb_lay_of<LAY>(a), y, cx.xp);
   hb_finish<D, I>(a, i, y, cx, flag);
 }
 // evolveHam over a shared time grid; out[k] = batch at ts[k]
@@ -912,7 +960,7 @@ HB_DEV void hb_traj_evolve(const HbKArgs& a, I i, const double* yin, const doubl
   constexpr int D = 2 * S::N;
   double y[D];
   hb_copy<D>(yin, y);
-  if (!FAST || !cx.oob) hb_store<D, I>(a.out, i, (I)a.N, hb_lay_of<LAY>(a), y);   // row 0 is the initial state
+  if (!FAST || !cx.oob) hb_store<D, I>(a.out, i, (I)a.N, hb_lay_of<LAY>(a), y, cx.xp);   // row 0 is the initial state
   int flag = 0;
   HbEvolve<D> e;
   e.h = (a.ts[1] - a.ts[0]) / 100;
@@ -929,7 +977,7 @@ HB_DEV void hb_traj_evolve(const HbKArgs& a, I i, const double* yin, const doubl
       t = tk;
     }
     if (FAST && cx.oob) return;   // rows written so far are rewritten by the slow retry (out never aliases in)
-    hb_store<D, I>(a.out + (size_t)k * (size_t)a.N * D, i, (I)a.N, hb_lay_of<LAY>(a), y);
+    hb_store<D, I>(a.out + (size_t)k * (size_t)a.N * D, i, (I)a.N, hb_lay_of<LAY>(a), y, cx.xp);
   }
   hb_finish<D, I>(a, i, y, cx, flag);
 }
@@ -946,7 +994,7 @@ HB_DEV void hb_traj_ham_eqs(const HbKArgs& a, I i, const double* yin, const doub
   int flag = 0;
   hb_rhs<S, FAST>(cx, a.prm, w, y, dy, flag);
   if (FAST && cx.oob) return;
-  hb_store<D, I>(a.out, i, (I)a.N, hb_lay_of<LAY>(a), dy);
+  hb_store<D, I>(a.out, i, (I)a.N, hb_lay_of<LAY>(a), dy, cx.xp);
   hb_finish<D, I>(a, i, dy, cx, flag);
 }
 template <class S, bool FAST, int LAY, class I>
@@ -958,7 +1006,7 @@ HB_DEV void hb_traj_to_phase(const HbKArgs& a, I i, const double* yin, const dou
   for (int j = 0; j < N; j++) y[j] = c[j];
   hb_momenta<S, FAST>(cx, a.prm, w, c, c + N, y + N);
   if (FAST && cx.oob) return;
-  hb_store<D, I>(a.out, i, (I)a.N, hb_lay_of<LAY>(a), y);
+  hb_store<D, I>(a.out, i, (I)a.N, hb_lay_of<LAY>(a), y, cx.xp);
 }
 template <class S, bool FAST, int LAY, class I>
 HB_DEV void hb_traj_from_phase(const HbKArgs& a, I i, const double* yin, const double* w, HbCtx& cx) {   // Phase [q, p] -> Config [q, v]
@@ -971,7 +1019,7 @@ HB_DEV void hb_traj_from_phase(const HbKArgs& a, I i, const double* yin, const d
   for (int j = 0; j < N; j++) c[j] = y[j];
   hb_velocities<S, FAST, false>(cx, a.prm, w, y, y + N, c + N, U, flag);
   if (FAST && cx.oob) return;
-  hb_store<D, I>(a.out, i, (I)a.N, hb_lay_of<LAY>(a), c);
+  hb_store<D, I>(a.out, i, (I)a.N, hb_lay_of<LAY>(a), c, cx.xp);
   hb_finish<D, I>(a, i, c, cx, flag);
 }
 // out4[i] = (keP, pe, hamiltonian, lagrangian)
@@ -989,7 +1037,7 @@ HB_DEV void hb_traj_energies(const HbKArgs& a, I i, const double* yin, const dou
   for (int j = 0; j < N; j++) T = fma(v[j], y[N + j], T);
   T *= 0.5;   // (vs <.> ps) / 2, src/Numeric/Hamilton.hs:349
   double o[4] = {T, U, T + U, T - U};
-  hb_store<4, I>(a.out, i, (I)a.N, a.layout == 2 ? 2 : 0, o);
+  hb_store<4, I>(a.out, i, (I)a.N, a.layout == 2 ? 2 : 0, o, cx.xp);
   hb_finish<4, I>(a, i, o, cx, flag);
 }
 template <class S, bool FAST, int LAY, class I>
@@ -1000,7 +1048,7 @@ HB_DEV void hb_traj_upos(const HbKArgs& a, I i, const double* yin, const double*
   hb_copy<N>(yin, q);
   S::template pos<FAST>(cx, a.prm, q, x);
   if (FAST && cx.oob) return;
-  hb_store<M, I>(a.out, i, (I)a.N, hb_lay_of<LAY>(a), x);
+  hb_store<M, I>(a.out, i, (I)a.N, hb_lay_of<LAY>(a), x, cx.xp);
 }
 
 // Kernel body = fast path inline + out-of-line slow retry for the rare out-of-domain trajectory.  DIN = doubles loaded
@@ -1020,6 +1068,7 @@ HB_DEV void hb_traj_upos(const HbKArgs& a, I i, const double* yin, const double*
   {                                                                                                        \
     HbCtx cx;                                                                                              \
     cx.tab_s = tab_s;                                                                                      \
+    cx.xp = xp;                                                                                            \
     hb_ctx_reset(cx);                                                                                      \
     HB_TRAJ_CALL_##NAME(IDX, YBUF)                                                                         \
     if (cx.oob) hb_slow_##NAME<S>(a, (long long)(IDX));                                                    \
@@ -1033,7 +1082,8 @@ HB_DEV void hb_traj_upos(const HbKArgs& a, I i, const double* yin, const double*
 #define HB_TRAJ_CALL_from_phase(IDX, YBUF) hb_traj_from_phase<S, true, LAY, unsigned>(a, IDX, YBUF, w, cx);
 #define HB_TRAJ_CALL_energies(IDX, YBUF) hb_traj_energies<S, true, LAY, unsigned>(a, IDX, YBUF, w, cx);
 #define HB_TRAJ_CALL_upos(IDX, YBUF) hb_traj_upos<S, true, LAY, unsigned>(a, IDX, YBUF, w, cx);
-#define HB_KERNEL_BODY(NAME, DIN_EXPR)                                                                     \
+// DIN / DOUT = doubles loaded / stored per trajectory.  big_tab: the statically allocated table of large systems.
+#define HB_KERNEL_BODY(NAME, DIN_EXPR, DOUT_EXPR)                                                          \
   template <class S>                                                                                       \
   __device__ __noinline__ void hb_slow_##NAME(const HbKArgs& a, long long i) {                             \
     constexpr int DIN = DIN_EXPR;                                                                          \
@@ -1042,16 +1092,24 @@ HB_DEV void hb_traj_upos(const HbKArgs& a, I i, const double* yin, const double*
     hb_load<DIN, long long>(a.in, i, a.N, a.layout, yin);                                                  \
     HbCtx cx;                                                                                              \
     cx.tab_s = 0;                                                                                          \
+    cx.xp = nullptr;                                                                                       \
     hb_ctx_reset(cx);                                                                                      \
     hb_traj_##NAME<S, false, -1, long long>(a, i, yin, w, cx);                                             \
   }                                                                                                        \
   template <class S, int LAY, int NST = 0>                                                                 \
-  HB_DEV void hb_body_##NAME(const HbKArgs& a, HbTab* tab) {                                               \
-    constexpr int DIN = DIN_EXPR;                                                                          \
+  HB_DEV void hb_body_##NAME(const HbKArgs& a, HbTab* big_tab) {                                           \
+    constexpr int DIN = DIN_EXPR, DOUT = DOUT_EXPR;                                                        \
+    constexpr bool SMALL = S::N < HB_BIG_N;                                                                \
+    constexpr bool ASYNC = SMALL && HB_ASYNC_STAGE && DIN % 2 == 0;                                        \
     const unsigned N = (unsigned)a.N;                                                                      \
     const unsigned istride = gridDim.x * blockDim.x;   /* trajectories per round */                        \
     unsigned i = (blockIdx.x + gridDim.x * (threadIdx.x >> 5)) * 32u + (threadIdx.x & 31u);                \
     const int lay = hb_lay_of<LAY>(a);                                                                     \
+    /* carve the dynamic shared memory (layout: HB_DYN_DOUBLES) */                                         \
+    HbTab* tab = SMALL ? reinterpret_cast<HbTab*>(hb_dsm) : big_tab;                                       \
+    double* stage = hb_dsm + HB_TAB_BYTES / 8;                                                             \
+    double* xp = SMALL ? stage + 2 * DIN * blockDim.x : hb_dsm + HB_DYN_DOUBLES(S::N, S::NE) * blockDim.x; \
+    xp = (lay == 2 && DOUT % 2 == 0 && DOUT <= HB_WSTORE_MAXD) ? xp + (threadIdx.x & ~31u) * DOUT : nullptr; \
     HB_PDL_LAUNCH_DEPENDENTS();                                                                            \
     if constexpr (S::TRIG) hb_tab_issue(tab);                                                              \
     if constexpr (HB_PRE_L2) {                                                                             \
@@ -1064,21 +1122,21 @@ HB_DEV void hb_traj_upos(const HbKArgs& a, I i, const double* yin, const double*
     S::inertia(a.prm, w);                                                                                  \
     const unsigned tab_s = hb_smem_addr(tab);                                                              \
     bool more = i < N;                                                                                     \
-    if constexpr (HB_PINGPONG && DIN <= 8) {                                                               \
-      double ya[DIN], yb[DIN];                                                                             \
-      if (more) hb_load<DIN, unsigned>(a.in, i, N, lay, ya);                                               \
+    if (ASYNC && lay != 1) {   /* array of records: the next Phase lands in shared memory under this one's arithmetic */ \
+      const unsigned cstride = blockDim.x * 16u, sz = DIN * blockDim.x;   /* doubles per stage buffer */   \
+      double* cur = stage + threadIdx.x * 2;                                                               \
+      double* nxt = cur + sz;                                                                              \
+      unsigned cur_s = hb_smem_addr(cur), nxt_s = cur_s + sz * 8u;                                         \
+      if (more) hb_async_load<DIN>(cur, cur_s, cstride, a.in + (size_t)i * DIN);                           \
       while (more) {                                                                                       \
-        unsigned inext = i + istride;                                                                      \
+        double yin[DIN];                                                                                   \
+        hb_async_read<DIN>(cur, cur_s, cstride, yin);                                                      \
+        const unsigned inext = i + istride;                                                                \
         more = inext < N;                                                                                  \
-        if (more) hb_load<DIN, unsigned>(a.in, inext, N, lay, yb);                                         \
-        HB_PROCESS_(NAME, i, ya)                                                                           \
-        if (!more) break;                                                                                  \
+        if (more) hb_async_load<DIN>(nxt, nxt_s, cstride, a.in + (size_t)inext * DIN);                     \
+        HB_PROCESS_(NAME, i, yin)                                                                          \
         i = inext;                                                                                         \
-        inext = i + istride;                                                                               \
-        more = inext < N;                                                                                  \
-        if (more) hb_load<DIN, unsigned>(a.in, inext, N, lay, ya);                                         \
-        HB_PROCESS_(NAME, i, yb)                                                                           \
-        i = inext;                                                                                         \
+        { double* tp = cur; cur = nxt; nxt = tp; const unsigned ts = cur_s; cur_s = nxt_s; nxt_s = ts; }   \
       }                                                                                                    \
     } else {                                                                                               \
       double yin[DIN];                                                                                     \
@@ -1091,15 +1149,15 @@ HB_DEV void hb_traj_upos(const HbKArgs& a, I i, const double* yin, const double*
       }                                                                                                    \
     }                                                                                                      \
   }
-HB_KERNEL_BODY(step_rk4, 2 * S::N)
-HB_KERNEL_BODY(step_rkf45, 2 * S::N)
-HB_KERNEL_BODY(evolve_rk4, 2 * S::N)
-HB_KERNEL_BODY(evolve_rkf45, 2 * S::N)
-HB_KERNEL_BODY(ham_eqs, 2 * S::N)
-HB_KERNEL_BODY(to_phase, 2 * S::N)
-HB_KERNEL_BODY(from_phase, 2 * S::N)
-HB_KERNEL_BODY(energies, 2 * S::N)
-HB_KERNEL_BODY(upos, S::N)
+HB_KERNEL_BODY(step_rk4, 2 * S::N, 2 * S::N)
+HB_KERNEL_BODY(step_rkf45, 2 * S::N, 2 * S::N)
+HB_KERNEL_BODY(evolve_rk4, 2 * S::N, 2 * S::N)
+HB_KERNEL_BODY(evolve_rkf45, 2 * S::N, 2 * S::N)
+HB_KERNEL_BODY(ham_eqs, 2 * S::N, 2 * S::N)
+HB_KERNEL_BODY(to_phase, 2 * S::N, 2 * S::N)
+HB_KERNEL_BODY(from_phase, 2 * S::N, 2 * S::N)
+HB_KERNEL_BODY(energies, 2 * S::N, 4)
+HB_KERNEL_BODY(upos, S::N, S::M)
 
 // Counter-based initial Phases; D = a.nsteps, lo = prm[0..D), hi = prm[D..2D)
 HB_DEV double hb_splitmix_u01(unsigned long long z) {
@@ -1144,7 +1202,7 @@ HB_DEV void hb_body_init_random(const HbKArgs& a) {
 // Instantiates per-system __global__ kernels with C linkage names PFX_<kind>.  The sin/cos table image is declared here,
 // once per kernel, and handed to the body (systems without sin/cos reserve nothing).
 #define HB_TAB_DECL(SYS)                                                                          \
-  __shared__ __align__(128) unsigned char hb_tab_raw[SYS::TRIG ? sizeof(HbTab) : 16];             \
+  __shared__ __align__(128) unsigned char hb_tab_raw[(SYS::TRIG && SYS::N >= HB_BIG_N) ? sizeof(HbTab) : 16]; \
   HbTab* hb_tab = reinterpret_cast<HbTab*>(hb_tab_raw)
 // step kernels: one instance per layout class, picked once per launch (large systems: the step dwarfs the bookkeeping; one
 // instance keeps compile time)

@@ -41,6 +41,7 @@ static const char* const KERNEL_KINDS[K_COUNT] = {"step_rk4", "step_rkf45", "evo
 #define HB_WSTORE_MAXD 8   // must match engine/hb_engine.cuh
 #define HB_DYN_DOUBLES(NCOORD, NE_) ((NCOORD) >= HB_BIG_N ? 3 * 2 * (NCOORD) + (NE_) : 0)
 #define HB_MAXBLOCK_OF(NCOORD) HB_BLOCK_OF(NCOORD)
+#define HB_TAB_BYTES 32896   // must match engine/hb_engine.cuh
 #define HB_MAX_LAUNCH_N ((int64_t)0x7C000000)   // 2^31 - 2^26: i + (trajectories per round) stays below 2^32 in the kernels
 
 // from aot_kernels.cu
@@ -357,18 +358,23 @@ thread_local Scratch g_scratch;
 // Resident CTA slots of a kernel on the current device (SMs x occupancy), cached per (device, function).
 int resident_ctas(const void* fn, int block, size_t dyn_smem) {
   static std::mutex mu;
-  static std::map<std::tuple<int, const void*, int>, int> cache;
+  static std::map<std::tuple<int, const void*, int, size_t>, int> cache;
+  static std::map<std::pair<int, const void*>, size_t> max_dyn;   // opt-in dynamic shared memory already granted per function
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;
   std::lock_guard<std::mutex> lk(mu);
-  auto it = cache.find(std::make_tuple(dev, fn, block));
+  auto it = cache.find(std::make_tuple(dev, fn, block, dyn_smem));
   if (it != cache.end()) return it->second;
   int sms = 0, per_sm = 0;
-  if (dyn_smem > 48 * 1024 && cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem) != cudaSuccess) { cudaGetLastError(); return -1; }
+  size_t& granted = max_dyn[std::make_pair(dev, fn)];
+  if (dyn_smem > 48 * 1024 && dyn_smem > granted) {
+    if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem) != cudaSuccess) { cudaGetLastError(); return -1; }
+    granted = dyn_smem;
+  }
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, block, dyn_smem) != cudaSuccess) { cudaGetLastError(); return 0; }
   const int slots = sms * (per_sm > 0 ? per_sm : 1);
-  cache[std::make_tuple(dev, fn, block)] = slots;
+  cache[std::make_tuple(dev, fn, block, dyn_smem)] = slots;
   return slots;
 }
 
@@ -379,18 +385,11 @@ int resident_ctas(const void* fn, int block, size_t dyn_smem) {
 // first thing and griddepcontrol.wait before their first global read, so in a stream (or captured graph) of back-to-back
 // steps the next kernel's launch latency, table staging and first L2 prefetches hide under this kernel's tail.
 // The kernels index trajectories with 32 bits: callers (run_batch) hand at most HB_MAX_LAUNCH_N trajectories per launch.
-hb_status launch(const void* fn, const HbKArgs& a, long long work_items, cudaStream_t st, int block = HB_BLOCK, int max_block = HB_BLOCK,
-                 int dyn_doubles = 0) {
+hb_status launch(const void* fn, const HbKArgs& a, long long work_items, cudaStream_t st, int block = HB_BLOCK, size_t dyn_smem = 0) {
   if (work_items <= 0) return HB_OK;
-  static const int block_env = [] { const char* e = std::getenv("HB_BLOCK"); int t = e ? std::atoi(e) : 0; return (t >= 32 && t <= 1024 && t % 32 == 0) ? t : 0; }();
-  // experiment knob: small systems only (shared-memory layouts of large ones assume HB_BLOCK_OF); a size above the kernel's
-  // __launch_bounds__ (HB_BLOCK_SMALL at compile time) makes the launch fail with an error, never run wrongly
-  (void)max_block;
-  if (block_env && dyn_doubles == 0) block = block_env;
   static const double waves_env = [] { const char* e = std::getenv("HB_GRID_WAVES"); double t = e ? std::atof(e) : 0.0; return (t > 0 && t <= 4096) ? t : 0.0; }();
   static const bool pdl = std::getenv("HB_NO_PDL") == nullptr;
   long long blocks = (work_items + block - 1) / block;
-  const size_t dyn_smem = (size_t)dyn_doubles * sizeof(double) * block;
   const int slots = resident_ctas(fn, block, dyn_smem);
   if (slots < 0) return fail(HB_ERR_CUDA, "kernel needs more dynamic shared memory than the device offers");
   const long long cap = (long long)((double)slots * (waves_env > 0 ? waves_env : 1.0));
@@ -410,6 +409,24 @@ hb_status launch(const void* fn, const HbKArgs& a, long long work_items, cudaStr
   cfg.numAttrs = pdl ? 1 : 0;
   CU(cudaLaunchKernelExC(&cfg, fn, args));
   return HB_OK;
+}
+
+// CTA size of a system's kernels.  HB_BLOCK is an experiment knob for small systems only (the shared-memory layouts of large
+// ones assume HB_BLOCK_OF); a size above the kernel's __launch_bounds__ (HB_BLOCK_SMALL at compile time) makes the launch
+// fail with an error, never run wrongly.
+int block_for(const hb_system* s) {
+  static const int block_env = [] { const char* e = std::getenv("HB_BLOCK"); int t = e ? std::atoi(e) : 0; return (t >= 32 && t <= 1024 && t % 32 == 0) ? t : 0; }();
+  return (block_env && s->n < HB_BIG_N) ? block_env : HB_BLOCK_OF(s->n);
+}
+// Dynamic shared memory of one launch; mirrors the layout documented at HB_DYN_DOUBLES in engine/hb_engine.cuh.
+size_t dyn_smem_bytes(const hb_system* s, int block, int in_d, int out_d, int kernel_layout) {
+  size_t b = s->n >= HB_BIG_N ? (size_t)s->dyn_doubles * sizeof(double) * block : (size_t)HB_TAB_BYTES + (size_t)2 * in_d * sizeof(double) * block;
+  if (kernel_layout == 2 && out_d % 2 == 0 && out_d <= HB_WSTORE_MAXD) b += (size_t)out_d * sizeof(double) * block;
+  return b;
+}
+hb_status launch_sys(const hb_system* s, const void* fn, const HbKArgs& a, long long n_traj, cudaStream_t st, int in_d, int out_d) {
+  const int block = block_for(s);
+  return launch(fn, a, n_traj, st, block, dyn_smem_bytes(s, block, in_d, out_d, a.layout));
 }
 
 void fill_params(const hb_system* s, HbKArgs& a) {
@@ -455,7 +472,7 @@ hb_status run_batch(const hb_system* sys, int kid, HbKArgs a, int64_t N, hb_mems
       CU(cudaMemcpyAsync(dts, ts, sizeof(double) * s, cudaMemcpyHostToDevice, st));   // ts is tiny; pageable copy is staged by the driver
       a.ts = dts;
     }
-    rc = launch(fn, a, N, st, HB_BLOCK_OF(sys->n), HB_MAXBLOCK_OF(sys->n), sys->dyn_doubles);
+    rc = launch_sys(sys, fn, a, N, st, in_d, out_d);
     if (dts) cudaFreeAsync(dts, st);
     return rc;
   }
@@ -483,7 +500,7 @@ hb_status run_batch(const hb_system* sys, int kid, HbKArgs a, int64_t N, hb_mems
       if (ts) { CU(cudaMemcpyAsync(dts, ts, sizeof(double) * s, cudaMemcpyHostToDevice, st)); a.ts = (const double*)dts; }
       a.in = (const double*)din_h; a.out = (double*)dout_h; a.flags = (int*)dfl_h;
       if (a.layout == HB_LAYOUT_AOS) a.layout = 2;   // warp-transposed stores (engine/hb_engine.cuh hb_store)
-      if ((rc = launch(fn, a, N, st, HB_BLOCK_OF(sys->n), HB_MAXBLOCK_OF(sys->n), sys->dyn_doubles))) return rc;
+      if ((rc = launch_sys(sys, fn, a, N, st, in_d, out_d))) return rc;
       CU(cudaStreamSynchronize(st));
       return HB_OK;
     }
@@ -525,8 +542,8 @@ hb_status run_batch(const hb_system* sys, int kid, HbKArgs a, int64_t N, hb_mems
   }
   cudaStream_t s_up = g_scratch.streams[0], s_k = g_scratch.streams[1], s_down = g_scratch.streams[2];
   if ((rc = g_scratch.need_events((int)(2 * chunks) + 1))) return rc;
-  const int blk = HB_BLOCK_OF(sys->n), max_blk = HB_MAXBLOCK_OF(sys->n);
-  if (resident_ctas(fn, blk, (size_t)sys->dyn_doubles * sizeof(double) * blk) < 0)   // (also keeps this query out of a capture)
+  const int blk = block_for(sys);
+  if (resident_ctas(fn, blk, dyn_smem_bytes(sys, blk, in_d, out_d, hybrid ? 2 : a.layout)) < 0)   // (also keeps this query out of a capture)
     return fail(HB_ERR_CUDA, "kernel needs more dynamic shared memory than the device offers");
   auto enqueue = [&]() -> hb_status {
     if (ts) {
@@ -558,7 +575,7 @@ hb_status run_batch(const hb_system* sys, int kid, HbKArgs a, int64_t N, hb_mems
         ac.flags = flags ? (int*)dfl_h + i0 : nullptr;   // read-modify-write in host memory, only for flagged trajectories
         ac.layout = 2;
       }
-      hb_status lrc = launch(fn, ac, chunks == 1 ? N : n, s_k, blk, max_blk, sys->dyn_doubles);
+      hb_status lrc = launch_sys(sys, fn, ac, chunks == 1 ? N : n, s_k, in_d, out_d);
       if (lrc) return lrc;
       if (hybrid) { if (c + 1 == chunks) { CU(cudaEventRecord(done, s_k)); CU(cudaStreamWaitEvent(s_down, done, 0)); } continue; }
       CU(cudaEventRecord(done, s_k));

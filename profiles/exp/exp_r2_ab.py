@@ -7,18 +7,16 @@ a graph of K launches ping-ponging between two buffers (a real stepping loop: L2
 import os, subprocess, sys
 VARIANTS = [
     ("default", {}),
+    ("r2a build: register ping-pong prefetch", {"HB_LIB_PATH": "profiles/ab_libs/lib_r2a_pingpong.so"}),
+    ("default (again)", {}),
+    ("no cp.async staging (plain loads)", {"HB_JIT_DEFINES": "HB_ASYNC_STAGE=0"}),
     ("2 waves", {"HB_GRID_WAVES": "2"}),
-    ("table 512 (13-instr sincos)", {"HB_JIT_DEFINES": "HB_SC_LOG2=9"}),
-    ("Cody-Waite 2 terms", {"HB_JIT_DEFINES": "HB_SC_CW2=1"}),
-    ("no ping-pong", {"HB_JIT_DEFINES": "HB_PINGPONG=0"}),
+    ("CTA 256 (6 warps/scheduler)", {"HB_JIT_DEFINES": "HB_BLOCK_SMALL=256", "HB_BLOCK": "256"}),
+    ("CTA 384 (6 warps/scheduler)", {"HB_JIT_DEFINES": "HB_BLOCK_SMALL=384", "HB_BLOCK": "384"}),
+    ("CTA 192", {"HB_JIT_DEFINES": "HB_BLOCK_SMALL=192", "HB_BLOCK": "192"}),
+    ("CTA 256, 2 waves", {"HB_JIT_DEFINES": "HB_BLOCK_SMALL=256", "HB_BLOCK": "256", "HB_GRID_WAVES": "2"}),
     ("no L2 prefetch before the wait", {"HB_JIT_DEFINES": "HB_PRE_L2=0"}),
-    ("table staged by loads, not cp.async.bulk", {"HB_JIT_DEFINES": "HB_TAB_BULK=0"}),
     ("no PDL", {"HB_NO_PDL": "1"}),
-    ("CTA 256", {"HB_JIT_DEFINES": "HB_BLOCK_SMALL=256", "HB_BLOCK": "256"}),
-    ("CTA 320", {"HB_JIT_DEFINES": "HB_BLOCK_SMALL=320", "HB_BLOCK": "320"}),
-    ("CTA 640", {"HB_JIT_DEFINES": "HB_BLOCK_SMALL=640", "HB_BLOCK": "640"}),
-    ("CTA 64", {"HB_BLOCK": "64"}),
-    ("min 6 CTAs/SM", {"HB_JIT_DEFINES": "HB_MINB_RK4=6"}),
 ]
 def worker(name, log2n):
     sys.path.insert(0, ".")
