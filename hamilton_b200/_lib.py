@@ -85,8 +85,20 @@ def lib():
     L.hb_evolve_ham.argtypes = [vp, dp, dp, dp, i32, dp]
     L.hb_step_ham_c.argtypes = [vp, dbl, dp, dp, dp, dp]
     L.hb_evolve_ham_c.argtypes = [vp, dp, dp, dp, i32, dp]
-    for nm in dir(L):
-        pass
+    if not hasattr(L, "hb_ensemble_create"):      # an older saved build loaded through HB_LIB_PATH (A/B runs only)
+        _lib = L
+        return L
+    L.hb_ensemble_create.argtypes = [vp, i32, ip, i64, C.POINTER(vp)]
+    L.hb_ensemble_free.argtypes = [vp]
+    L.hb_ensemble_free.restype = None
+    L.hb_ensemble_dims.argtypes = [vp, ip, C.POINTER(i64), C.POINTER(i64)]
+    L.hb_ensemble_init_random.argtypes = [vp, C.c_uint64, dp, dp]
+    L.hb_ensemble_upload.argtypes = [vp, vp]
+    L.hb_ensemble_step.argtypes = [vp, i32, dbl, i32, i32, dp]
+    L.hb_ensemble_gather.argtypes = [vp, vp, dp]
+    L.hb_ensemble_shard.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(i64)]
+    L.hb_ensemble_gathered.argtypes = [vp, i32, C.POINTER(vp)]
+    L.hb_ensemble_flags.argtypes = [vp, vp]
     _lib = L
     return L
 
@@ -109,4 +121,6 @@ ABI_SYMBOLS = [
     "hb_batch_to_phase", "hb_batch_from_phase", "hb_batch_energies", "hb_batch_underlying_pos", "hb_batch_init_random",
     "hb_underlying_pos", "hb_pe", "hb_momenta", "hb_velocities", "hb_ke_c", "hb_ke_p", "hb_lagrangian", "hb_hamiltonian",
     "hb_ham_eqs", "hb_step_ham", "hb_evolve_ham", "hb_step_ham_c", "hb_evolve_ham_c",
+    "hb_ensemble_create", "hb_ensemble_free", "hb_ensemble_dims", "hb_ensemble_init_random", "hb_ensemble_upload", "hb_ensemble_step",
+    "hb_ensemble_gather", "hb_ensemble_shard", "hb_ensemble_gathered", "hb_ensemble_flags",
 ]

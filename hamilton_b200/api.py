@@ -95,16 +95,17 @@ class System:
         return buf[:n]
 
     # ---- batched entry points ---------------------------------------------------------------
-    def _io(self, x, name):
-        """Returns (pointer, memspace, stream, device_ctx, keepalive, kind) for numpy or torch-cuda input."""
+    def _io(self, x, name, flags=False):
+        """Returns (pointer, memspace, device) for numpy or torch input; data arrays must be float64, flags int32 — the C
+        library reads and writes exactly N x d doubles (N int32 flags), so anything else would run past the buffer."""
         if isinstance(x, np.ndarray):
-            if x.dtype not in (np.float64, np.int32) or not x.flags["C_CONTIGUOUS"]:
-                raise ValueError("%s must be a C-contiguous float64 array" % name)
+            if x.dtype != (np.int32 if flags else np.float64) or not x.flags["C_CONTIGUOUS"]:
+                raise ValueError("%s must be a C-contiguous %s array" % (name, "int32" if flags else "float64"))
             return x.ctypes.data, L.HOST, None
         import torch
         if isinstance(x, torch.Tensor):
-            if x.dtype not in (torch.float64, torch.int32) or not x.is_contiguous():
-                raise ValueError("%s must be a contiguous float64 tensor" % name)
+            if x.dtype != (torch.int32 if flags else torch.float64) or not x.is_contiguous():
+                raise ValueError("%s must be a contiguous %s tensor" % (name, "int32" if flags else "float64"))
             if x.is_cuda:
                 return x.data_ptr(), L.DEVICE, x.device
             return x.data_ptr(), L.HOST, None     # CPU tensor (possibly pinned): host memspace
@@ -125,12 +126,20 @@ class System:
         dt = {None: torch.float64, np.int32: torch.int32}[dtype]
         return torch.empty(shape, dtype=dt, device=y.device, pin_memory=(not y.is_cuda and y.is_pinned()))
 
-    def _run(self, y, outs, call):
-        """call(mem, stream) -> status, with the device of `y` current and its torch stream passed through."""
+    def _run(self, y, outs, call, out_shape=None):
+        """call(mem, stream) -> status, with the device of `y` current and its torch stream passed through.
+        outs = [out, flags?]: `out` must have exactly `out_shape` (default: the shape of y), everything must live in the same
+        memory space and, on the GPU, on the same device."""
         ptr, mem, dev = self._io(y, "input")
-        for o in outs:
-            if o is not None and self._io(o, "output")[1] != mem:
-                raise ValueError("input, output and flags must live in the same memory space")
+        want = tuple(y.shape) if out_shape is None else tuple(out_shape)
+        for k, o in enumerate(outs):
+            if o is None:
+                continue
+            _, omem, odev = self._io(o, "flags" if k else "output", flags=bool(k))
+            if omem != mem or odev != dev:
+                raise ValueError("input, output and flags must live in the same memory space (and on the same device)")
+            if k == 0 and tuple(o.shape) != want:
+                raise ValueError("output has shape %s, expected %s" % (tuple(o.shape), want))
         if mem == L.DEVICE:
             import torch
             with torch.cuda.device(dev):
@@ -181,7 +190,7 @@ class System:
         self._flags_ok(flags, N)
         self._run(y0, [out, flags], lambda mem, st: L.lib().hb_batch_evolve(
             self._h, int(integ), int(rk4_substeps), N, int(layout), mem, self._vp(y0), _p(ts), ts.size, self._vp(out),
-            self._vp(flags), st))
+            self._vp(flags), st), out_shape=(ts.size,) + tuple(y0.shape))
         return out
 
     def batch_to_phase(self, c, layout=L.AOS, out=None):
@@ -207,14 +216,15 @@ class System:
             out = self._alloc_like(y, (N, 4))
         self._flags_ok(flags, N)
         self._run(y, [out, flags], lambda mem, st: L.lib().hb_batch_energies(
-            self._h, N, int(layout), mem, self._vp(y), self._vp(out), self._vp(flags), st))
+            self._h, N, int(layout), mem, self._vp(y), self._vp(out), self._vp(flags), st), out_shape=(N, 4))
         return out
 
     def batch_underlying_pos(self, q, layout=L.AOS, out=None):
         N = self._shape(q, self.n, layout, "q")
         if out is None:
             out = self._alloc_like(q, (N, self.m) if layout == L.AOS else (self.m, N))
-        self._run(q, [out], lambda mem, st: L.lib().hb_batch_underlying_pos(self._h, N, int(layout), mem, self._vp(q), self._vp(out), st))
+        self._run(q, [out], lambda mem, st: L.lib().hb_batch_underlying_pos(self._h, N, int(layout), mem, self._vp(q), self._vp(out), st),
+                  out_shape=(N, self.m) if layout == L.AOS else (self.m, N))
         return out
 
     def batch_init_random(self, seed, first, N, lo, hi, layout=L.AOS, device=None):

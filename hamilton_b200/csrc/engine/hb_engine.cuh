@@ -35,8 +35,12 @@
 #define HB_MAXP 64
 // Threads per CTA, fixed per system size (the host launches exactly this): 128 for small systems whose whole
 // state lives in registers and for n >= 8, where the RK vectors are staged in dynamic shared memory (HB_DYN_DOUBLES).
+// Small systems: the host picks the CTA size per launch (csrc/runtime.cpp pick_block): one CTA per SM of 8..16 warps when the
+// kernel's registers allow it — one 32 KB table image staged per SM per launch — with the warp count chosen so that the
+// batch's tiles divide into (nearly) whole rounds.  HB_BLOCK_SMALL is the upper bound the kernels are compiled for
+// (__launch_bounds__: 512 threads leave every kernel 128 registers).
 #ifndef HB_BLOCK_SMALL
-#define HB_BLOCK_SMALL 128   // CTA size of small systems (A/B switch; the host launches what HB_BLOCK says, <= this)
+#define HB_BLOCK_SMALL 512
 #endif
 #define HB_BLOCK_OF(NCOORD) ((NCOORD) >= HB_BIG_N ? 128 : HB_BLOCK_SMALL)
 // Large systems (n >= HB_BIG_N) keep the RK4 vectors (y, acc, stage input: 3 * 2n doubles per thread) and, for
@@ -83,6 +87,8 @@ struct HbKArgs {
   int substeps;           // evolve/RK4: equal sub-steps per grid interval
   unsigned long long seed;
   long long first;
+  int host_io;            // 1: `in` / `out` are page-locked HOST memory accessed over PCIe (no L2 prefetches of them)
+  int pad_;
   double prm[HB_MAXP];    // runtime parameters (HB_OP_PARAM leaves); for init_random: lo[0..D), hi[0..D)
 };
 
@@ -455,16 +461,20 @@ struct HbSmemVec {  // right-hand side parked in shared memory (element j at b[j
   const double* b;
   HB_DEV double operator()(int j) const { return hb_lds(b + j * STRIDE); }
 };
-template <int N, class BV>
+// CLOSED: use the closed forms for N <= 3 (fast path).  Their pivot test looks at the determinant, which under- or overflows
+// for inertias around 1e-160 / 1e+160 although the matrix is perfectly invertible (LAPACK's `inv` in the reference has no
+// such problem): a failed test on the fast path therefore only sends the trajectory to the out-of-line slow path
+// (hb_retry), which runs the scale-safe LDL^T for every N and raises HB_FLAG_NOT_SPD only if a pivot really is <= 0.
+template <int N, bool CLOSED, class BV>
 HB_DEV void hb_spd_solve_v(double* A, const BV b, double* x, int& minpiv);
-template <int N>
-HB_DEV void hb_spd_solve(double* A, const double* b, double* x, int& minpiv) { hb_spd_solve_v<N>(A, HbRegVec{b}, x, minpiv); }
-template <int N, class BV>
+template <int N, bool CLOSED>
+HB_DEV void hb_spd_solve(double* A, const double* b, double* x, int& minpiv) { hb_spd_solve_v<N, CLOSED>(A, HbRegVec{b}, x, minpiv); }
+template <int N, bool CLOSED, class BV>
 HB_DEV void hb_spd_solve_v(double* A, const BV b, double* x, int& minpiv) {
   if constexpr (N == 1) {
     hb_piv(minpiv, A[0]);
     x[0] = b(0) * hb_rcp(A[0]);
-  } else if constexpr (N == 2) {
+  } else if constexpr (N == 2 && CLOSED) {
     const double det = fma(A[0], A[2], -A[1] * A[1]);
     hb_piv(minpiv, A[0]);
     hb_piv(minpiv, det);
@@ -474,7 +484,7 @@ HB_DEV void hb_spd_solve_v(double* A, const BV b, double* x, int& minpiv) {
     x[0] = n0 * id;
     x[1] = n1 * id;
 #ifndef HB_SPD3_LDLT
-  } else if constexpr (N == 3) {
+  } else if constexpr (N == 3 && CLOSED) {
     // adjugate form: 6 cofactors, ONE reciprocal — a dependency chain of ~12 DFMA instead of LDL^T's three
     // back-to-back reciprocal chains (this engine runs at 4-6 warps per scheduler, so latency is throughput);
     // positive leading minors (a, ad - b^2, det) <=> SPD
@@ -567,7 +577,7 @@ HB_DEV void hb_ham_eqs_sym(HbCtx& cx, const double* prm, const double* qq, const
 #pragma unroll
       for (int e = 0; e < NE; e++) hb_sts(es + e * B, E[e]);
     }
-    hb_spd_solve_v<N>(A, p, dq, cx.minpiv);
+    hb_spd_solve_v<N, FAST>(A, p, dq, cx.minpiv);
     double E[NE];
 #pragma unroll
     for (int e = 0; e < NE; e++) E[e] = hb_lds(es + e * B);
@@ -575,7 +585,7 @@ HB_DEV void hb_ham_eqs_sym(HbCtx& cx, const double* prm, const double* qq, const
   } else {
     double E[NE > 0 ? NE : 1];
     S::template hpre<FAST>(cx, prm, qq, A, E);
-    hb_spd_solve_v<N>(A, p, dq, cx.minpiv);
+    hb_spd_solve_v<N, FAST>(A, p, dq, cx.minpiv);
     S::template hpost<FAST>(cx, prm, qq, E, dq, dp);
   }
 }
@@ -606,7 +616,7 @@ HB_DEV void hb_ham_eqs(HbCtx& cx, const double* prm, const double* w, const doub
   hb_weigh<S>(w, Jv, wJ);
   double A[N * (N + 1) / 2];
   hb_mass<S>(wJ, Jv, A);
-  hb_spd_solve<N>(A, p, dq, cx.minpiv);
+  hb_spd_solve<N, FAST>(A, p, dq, cx.minpiv);
   double a[M];
   hb_j_mul<S>(wJ, dq, a);
 #pragma unroll
@@ -667,14 +677,14 @@ HB_DEV void hb_velocities(HbCtx& cx, const double* prm, const double* w, const d
     (void)w;
     double A[N * (N + 1) / 2];
     if constexpr (WITH_U) S::template smass_pot<FAST>(cx, prm, qq, A, U); else S::template smass<FAST>(cx, prm, qq, A);
-    hb_spd_solve<N>(A, p, v, cx.minpiv);
+    hb_spd_solve<N, FAST>(A, p, v, cx.minpiv);
     return;
   }
   if constexpr (WITH_U) S::template jac_pot<FAST>(cx, prm, qq, Jv, U); else S::template jac<FAST>(cx, prm, qq, Jv);
   hb_weigh<S>(w, Jv, wJ);
   double A[N * (N + 1) / 2];
   hb_mass<S>(wJ, Jv, A);
-  hb_spd_solve<N>(A, p, v, cx.minpiv);
+  hb_spd_solve<N, FAST>(A, p, v, cx.minpiv);
 }
 
 // ------------------------------------------------------------------------ integrators ------
@@ -811,7 +821,7 @@ HB_DEV void hb_rkf45_to(HbCtx& cx, const double* prm, const double* w, double (&
                         HbEvolve<2 * S::N>& e, int& flag) {
   constexpr int D = 2 * S::N;
   typedef HbRkf45 T;
-  int guard = 0;
+  int guard = 0, attempts = 0;
   while (t < t1) {
     const double t0 = t;
     double h0 = e.h;
@@ -829,6 +839,9 @@ HB_DEV void hb_rkf45_to(HbCtx& cx, const double* prm, const double* w, double (&
       if ((dt >= 0.0 && h0 > dt) || (dt < 0.0 && h0 < dt)) { h0 = dt; final_step = true; } else final_step = false;
       hb_rkf45_apply<S, FAST>(cx, prm, w, h0, y, k1, yerr, dout, flag);
       t = final_step ? t1 : t0 + h0;
+      // GSL (and with it the reference) would spin forever on a step that does not advance t (h = 0 after a zero-length first
+      // grid interval, or h below the spacing of t); on a GPU that hangs the stream: give the trajectory up instead
+      if ((!final_step && t == t0) || ++attempts > 20000000) { flag |= HB_FLAG_STEP_FAILED; e.h = h0; t = t1; return; }
       // std_control_hadjust, ord = 5
       const double h_old = h0;
       // Shortcut for the common case: every error ratio <= 3.3e-5 implies rmax < 0.5 and 0.9 rmax^(-1/6) >= 5.02, which
@@ -891,12 +904,17 @@ HB_DEV void hb_rkf45_to(HbCtx& cx, const double* prm, const double* w, double (&
 #ifndef HB_LAYSPEC
 #define HB_LAYSPEC 1
 #endif
+#ifndef HB_L2_AHEAD
+#define HB_L2_AHEAD 0      // 1: besides the cp.async of the next Phase, pull the one after it into L2
+#endif
 #ifndef HB_ASYNC_STAGE
 #define HB_ASYNC_STAGE 1   // small systems, array of records: the next Phase is staged by cp.async into shared memory (0: plain loads)
 #endif
 template <int LAY> HB_DEV int hb_lay_of(const HbKArgs& a) { if constexpr (LAY < 0) return a.layout; else return LAY; }
 // HB_FLAG_* bits of one trajectory: what the integrators raised + the deferred pivot test
 HB_DEV int hb_ctx_flags(const HbCtx& cx, int flag) { return cx.minpiv < 0x00100000 ? (flag | HB_FLAG_NOT_SPD) : flag; }
+// fast path only: redo this trajectory out of line (argument outside a fast primitive's domain, or a failed pivot test)
+HB_DEV bool hb_retry(const HbCtx& cx) { return cx.oob != 0 || cx.minpiv < 0x00100000; }
 // Each hb_traj_* processes trajectory i completely (compute -> store; the kernel body loads).  FAST=true is inlined
 // into the kernel; if any fast primitive left its domain (cx.oob) nothing is stored and the kernel
 // re-runs that one trajectory through the out-of-line FAST=false instance (HB_KERNEL_BODY below).
@@ -930,7 +948,7 @@ HB_DEV void hb_traj_step_rk4(const HbKArgs& a, I i, const double* yin, const dou
     if constexpr (NST == 1) hb_rk4_step<S, FAST>(cx, a.prm, w, y, a.dt, a.dt6, a.dth, flag);
     else for (int s = 0; s < a.nsteps; s++) hb_rk4_step<S, FAST>(cx, a.prm, w, y, a.dt, a.dt6, a.dth, flag);
   }
-  if (FAST && cx.oob) return;
+  if (FAST && hb_retry(cx)) return;
   hb_store<D, I>(a.out, i, (I)a.N, hb_lay_of<LAY>(a), y, cx.xp);
   hb_finish<D, I>(a, i, y, cx, flag);
 }
@@ -950,7 +968,7 @@ HB_DEV void hb_traj_step_rkf45(const HbKArgs& a, I i, const double* yin, const d
       hb_rkf45_to<S, FAST>(cx, a.prm, w, y, t, a.dt, e, flag);
     }
   }
-  if (FAST && cx.oob) return;
+  if (FAST && hb_retry(cx)) return;
   hb_store<D, I>(a.out, i, (I)a.N, hb_lay_of<LAY>(a), y, cx.xp);
   hb_finish<D, I>(a, i, y, cx, flag);
 }
@@ -960,7 +978,7 @@ HB_DEV void hb_traj_evolve(const HbKArgs& a, I i, const double* yin, const doubl
   constexpr int D = 2 * S::N;
   double y[D];
   hb_copy<D>(yin, y);
-  if (!FAST || !cx.oob) hb_store<D, I>(a.out, i, (I)a.N, hb_lay_of<LAY>(a), y, cx.xp);   // row 0 is the initial state
+  if (!FAST || !hb_retry(cx)) hb_store<D, I>(a.out, i, (I)a.N, hb_lay_of<LAY>(a), y, cx.xp);   // row 0 is the initial state
   int flag = 0;
   HbEvolve<D> e;
   e.h = (a.ts[1] - a.ts[0]) / 100;
@@ -976,7 +994,7 @@ HB_DEV void hb_traj_evolve(const HbKArgs& a, I i, const double* yin, const doubl
       for (int s = 0; s < a.substeps; s++) hb_rk4_step<S, FAST>(cx, a.prm, w, y, h, h6, 0.5 * h, flag);
       t = tk;
     }
-    if (FAST && cx.oob) return;   // rows written so far are rewritten by the slow retry (out never aliases in)
+    if (FAST && hb_retry(cx)) return;   // rows written so far are rewritten by the slow retry (out never aliases in)
     hb_store<D, I>(a.out + (size_t)k * (size_t)a.N * D, i, (I)a.N, hb_lay_of<LAY>(a), y, cx.xp);
   }
   hb_finish<D, I>(a, i, y, cx, flag);
@@ -993,7 +1011,7 @@ HB_DEV void hb_traj_ham_eqs(const HbKArgs& a, I i, const double* yin, const doub
   hb_copy<D>(yin, y);
   int flag = 0;
   hb_rhs<S, FAST>(cx, a.prm, w, y, dy, flag);
-  if (FAST && cx.oob) return;
+  if (FAST && hb_retry(cx)) return;
   hb_store<D, I>(a.out, i, (I)a.N, hb_lay_of<LAY>(a), dy, cx.xp);
   hb_finish<D, I>(a, i, dy, cx, flag);
 }
@@ -1005,7 +1023,7 @@ HB_DEV void hb_traj_to_phase(const HbKArgs& a, I i, const double* yin, const dou
 #pragma unroll
   for (int j = 0; j < N; j++) y[j] = c[j];
   hb_momenta<S, FAST>(cx, a.prm, w, c, c + N, y + N);
-  if (FAST && cx.oob) return;
+  if (FAST && hb_retry(cx)) return;
   hb_store<D, I>(a.out, i, (I)a.N, hb_lay_of<LAY>(a), y, cx.xp);
 }
 template <class S, bool FAST, int LAY, class I>
@@ -1018,7 +1036,7 @@ HB_DEV void hb_traj_from_phase(const HbKArgs& a, I i, const double* yin, const d
 #pragma unroll
   for (int j = 0; j < N; j++) c[j] = y[j];
   hb_velocities<S, FAST, false>(cx, a.prm, w, y, y + N, c + N, U, flag);
-  if (FAST && cx.oob) return;
+  if (FAST && hb_retry(cx)) return;
   hb_store<D, I>(a.out, i, (I)a.N, hb_lay_of<LAY>(a), c, cx.xp);
   hb_finish<D, I>(a, i, c, cx, flag);
 }
@@ -1031,7 +1049,7 @@ HB_DEV void hb_traj_energies(const HbKArgs& a, I i, const double* yin, const dou
   int flag = 0;
   double U;
   hb_velocities<S, FAST, true>(cx, a.prm, w, y, y + N, v, U, flag);
-  if (FAST && cx.oob) return;
+  if (FAST && hb_retry(cx)) return;
   double T = 0.0;
 #pragma unroll
   for (int j = 0; j < N; j++) T = fma(v[j], y[N + j], T);
@@ -1047,7 +1065,7 @@ HB_DEV void hb_traj_upos(const HbKArgs& a, I i, const double* yin, const double*
   (void)w;
   hb_copy<N>(yin, q);
   S::template pos<FAST>(cx, a.prm, q, x);
-  if (FAST && cx.oob) return;
+  if (FAST && hb_retry(cx)) return;
   hb_store<M, I>(a.out, i, (I)a.N, hb_lay_of<LAY>(a), x, cx.xp);
 }
 
@@ -1071,7 +1089,7 @@ HB_DEV void hb_traj_upos(const HbKArgs& a, I i, const double* yin, const double*
     cx.xp = xp;                                                                                            \
     hb_ctx_reset(cx);                                                                                      \
     HB_TRAJ_CALL_##NAME(IDX, YBUF)                                                                         \
-    if (cx.oob) hb_slow_##NAME<S>(a, (long long)(IDX));                                                    \
+    if (hb_retry(cx)) hb_slow_##NAME<S>(a, (long long)(IDX));                                              \
   }
 #define HB_TRAJ_CALL_step_rk4(IDX, YBUF) hb_traj_step_rk4<S, true, LAY, unsigned, NST>(a, IDX, YBUF, w, cx);
 #define HB_TRAJ_CALL_step_rkf45(IDX, YBUF) hb_traj_step_rkf45<S, true, LAY, unsigned>(a, IDX, YBUF, w, cx);
@@ -1083,7 +1101,7 @@ HB_DEV void hb_traj_upos(const HbKArgs& a, I i, const double* yin, const double*
 #define HB_TRAJ_CALL_energies(IDX, YBUF) hb_traj_energies<S, true, LAY, unsigned>(a, IDX, YBUF, w, cx);
 #define HB_TRAJ_CALL_upos(IDX, YBUF) hb_traj_upos<S, true, LAY, unsigned>(a, IDX, YBUF, w, cx);
 // DIN / DOUT = doubles loaded / stored per trajectory.  big_tab: the statically allocated table of large systems.
-#define HB_KERNEL_BODY(NAME, DIN_EXPR, DOUT_EXPR)                                                          \
+#define HB_KERNEL_BODY(NAME, DIN_EXPR, DOUT_EXPR, STEPPING)                                                \
   template <class S>                                                                                       \
   __device__ __noinline__ void hb_slow_##NAME(const HbKArgs& a, long long i) {                             \
     constexpr int DIN = DIN_EXPR;                                                                          \
@@ -1100,7 +1118,8 @@ HB_DEV void hb_traj_upos(const HbKArgs& a, I i, const double* yin, const double*
   HB_DEV void hb_body_##NAME(const HbKArgs& a, HbTab* big_tab) {                                           \
     constexpr int DIN = DIN_EXPR, DOUT = DOUT_EXPR;                                                        \
     constexpr bool SMALL = S::N < HB_BIG_N;                                                                \
-    constexpr bool ASYNC = SMALL && HB_ASYNC_STAGE && DIN % 2 == 0;                                        \
+    /* cp.async staging only where a trajectory costs clearly more issue time than HBM time (Sys::HEAVY, stepping kernels) */ \
+    constexpr bool ASYNC = SMALL && HB_ASYNC_STAGE && DIN % 2 == 0 && STEPPING && S::HEAVY;                \
     const unsigned N = (unsigned)a.N;                                                                      \
     const unsigned istride = gridDim.x * blockDim.x;   /* trajectories per round */                        \
     unsigned i = (blockIdx.x + gridDim.x * (threadIdx.x >> 5)) * 32u + (threadIdx.x & 31u);                \
@@ -1112,7 +1131,7 @@ HB_DEV void hb_traj_upos(const HbKArgs& a, I i, const double* yin, const double*
     xp = (lay == 2 && DOUT % 2 == 0 && DOUT <= HB_WSTORE_MAXD) ? xp + (threadIdx.x & ~31u) * DOUT : nullptr; \
     HB_PDL_LAUNCH_DEPENDENTS();                                                                            \
     if constexpr (S::TRIG) hb_tab_issue(tab);                                                              \
-    if constexpr (HB_PRE_L2) {                                                                             \
+    if (HB_PRE_L2 && !a.host_io) {                                                                         \
       if (i < N) hb_prefetch_l2<DIN, unsigned>(a.in, i, N, lay);                                           \
       if (i + istride < N) hb_prefetch_l2<DIN, unsigned>(a.in, i + istride, N, lay);                       \
     }                                                                                                      \
@@ -1122,7 +1141,7 @@ HB_DEV void hb_traj_upos(const HbKArgs& a, I i, const double* yin, const double*
     S::inertia(a.prm, w);                                                                                  \
     const unsigned tab_s = hb_smem_addr(tab);                                                              \
     bool more = i < N;                                                                                     \
-    if (ASYNC && lay != 1) {   /* array of records: the next Phase lands in shared memory under this one's arithmetic */ \
+    if (ASYNC && lay != 1 && !a.host_io) {   /* array of records in device memory: the next Phase lands in shared memory under this one's arithmetic (over PCIe cp.async runs at a quarter of the rate of plain loads: profiles/r2c) */ \
       const unsigned cstride = blockDim.x * 16u, sz = DIN * blockDim.x;   /* doubles per stage buffer */   \
       double* cur = stage + threadIdx.x * 2;                                                               \
       double* nxt = cur + sz;                                                                              \
@@ -1134,6 +1153,7 @@ HB_DEV void hb_traj_upos(const HbKArgs& a, I i, const double* yin, const double*
         const unsigned inext = i + istride;                                                                \
         more = inext < N;                                                                                  \
         if (more) hb_async_load<DIN>(nxt, nxt_s, cstride, a.in + (size_t)inext * DIN);                     \
+        if (HB_L2_AHEAD && !a.host_io) { if (inext + istride < N) hb_prefetch_l2<DIN, unsigned>(a.in, inext + istride, N, lay); } \
         HB_PROCESS_(NAME, i, yin)                                                                          \
         i = inext;                                                                                         \
         { double* tp = cur; cur = nxt; nxt = tp; const unsigned ts = cur_s; cur_s = nxt_s; nxt_s = ts; }   \
@@ -1142,22 +1162,22 @@ HB_DEV void hb_traj_upos(const HbKArgs& a, I i, const double* yin, const double*
       double yin[DIN];                                                                                     \
       while (more) {                                                                                       \
         hb_load<DIN, unsigned>(a.in, i, N, lay, yin);                                                      \
-        if constexpr (HB_PRE_L2) { if (i + 2 * istride < N) hb_prefetch_l2<DIN, unsigned>(a.in, i + 2 * istride, N, lay); } \
+        if (HB_PRE_L2 && !a.host_io) { if (i + 2 * istride < N) hb_prefetch_l2<DIN, unsigned>(a.in, i + 2 * istride, N, lay); } \
         HB_PROCESS_(NAME, i, yin)                                                                          \
         i += istride;                                                                                      \
         more = i < N;                                                                                      \
       }                                                                                                    \
     }                                                                                                      \
   }
-HB_KERNEL_BODY(step_rk4, 2 * S::N, 2 * S::N)
-HB_KERNEL_BODY(step_rkf45, 2 * S::N, 2 * S::N)
-HB_KERNEL_BODY(evolve_rk4, 2 * S::N, 2 * S::N)
-HB_KERNEL_BODY(evolve_rkf45, 2 * S::N, 2 * S::N)
-HB_KERNEL_BODY(ham_eqs, 2 * S::N, 2 * S::N)
-HB_KERNEL_BODY(to_phase, 2 * S::N, 2 * S::N)
-HB_KERNEL_BODY(from_phase, 2 * S::N, 2 * S::N)
-HB_KERNEL_BODY(energies, 2 * S::N, 4)
-HB_KERNEL_BODY(upos, S::N, S::M)
+HB_KERNEL_BODY(step_rk4, 2 * S::N, 2 * S::N, true)
+HB_KERNEL_BODY(step_rkf45, 2 * S::N, 2 * S::N, true)
+HB_KERNEL_BODY(evolve_rk4, 2 * S::N, 2 * S::N, true)
+HB_KERNEL_BODY(evolve_rkf45, 2 * S::N, 2 * S::N, true)
+HB_KERNEL_BODY(ham_eqs, 2 * S::N, 2 * S::N, false)
+HB_KERNEL_BODY(to_phase, 2 * S::N, 2 * S::N, false)
+HB_KERNEL_BODY(from_phase, 2 * S::N, 2 * S::N, false)
+HB_KERNEL_BODY(energies, 2 * S::N, 4, false)
+HB_KERNEL_BODY(upos, S::N, S::M, false)
 
 // Counter-based initial Phases; D = a.nsteps, lo = prm[0..D), hi = prm[D..2D)
 HB_DEV double hb_splitmix_u01(unsigned long long z) {
@@ -1224,7 +1244,7 @@ HB_DEV void hb_body_init_random(const HbKArgs& a) {
 // The adaptive kernels keep six stage vectors live and reach 200+ registers (2 CTAs/SM: two warps per scheduler cannot
 // cover the 8-clock FP64 latency).  Capping small systems at 128 registers (4 CTAs/SM) spills a few stage vectors to
 // local memory and still wins: double pendulum +10 %, triple pendulum +11 % (profiles/r1z/ab_rkf45_regs.txt).
-#define HB_LB_RKF45(SYS) __launch_bounds__(HB_MAXBLOCK_OF(SYS::N), (SYS::N <= 3 ? 512 / HB_MAXBLOCK_OF(SYS::N) : 0))
+#define HB_LB_RKF45(SYS) __launch_bounds__((SYS::N <= 3 ? 256 : HB_MAXBLOCK_OF(SYS::N)), (SYS::N <= 3 ? 2 : 0))
 #endif
 #define HB_DEFINE_KERNEL_Y(SYS, PFX, KIND) extern "C" __global__ void HB_LB_RKF45(SYS) PFX##_##KIND(const __grid_constant__ HbKArgs a) { HB_TAB_DECL(SYS); hb_body_##KIND<SYS, -1>(a, hb_tab); }
 #define HB_DEFINE_KERNEL_step_rkf45(SYS, PFX) HB_DEFINE_KERNEL_L(SYS, PFX, step_rkf45, HB_LB_RKF45(SYS), 0)

@@ -30,13 +30,14 @@ struct HbKArgs {
   const double* in; double* out; int* flags; const double* ts;
   long long N; double dt; double dt6; double dth; int nsteps; int layout; int s; int substeps;
   unsigned long long seed; long long first;
+  int host_io; int pad_;
   double prm[HB_MAXP];
 };
 enum { K_STEP_RK4 = 0, K_STEP_RKF45, K_EVOLVE_RK4, K_EVOLVE_RKF45, K_HAM_EQS, K_TO_PHASE, K_FROM_PHASE, K_ENERGIES, K_UPOS, K_COUNT };
 static const char* const KERNEL_KINDS[K_COUNT] = {"step_rk4", "step_rkf45", "evolve_rk4", "evolve_rkf45", "ham_eqs",
                                                   "to_phase", "from_phase", "energies", "upos"};
 #define HB_BLOCK 128
-#define HB_BLOCK_OF(NCOORD) 128   // must match engine/hb_engine.cuh
+#define HB_BLOCK_OF(NCOORD) 128   // large systems (n >= HB_BIG_N); must match engine/hb_engine.cuh
 #define HB_BIG_N 8
 #define HB_WSTORE_MAXD 8   // must match engine/hb_engine.cuh
 #define HB_DYN_DOUBLES(NCOORD, NE_) ((NCOORD) >= HB_BIG_N ? 3 * 2 * (NCOORD) + (NE_) : 0)
@@ -236,6 +237,8 @@ struct hb_system {
   bool baked = false;                  // built-in with the default parameters: use the literal-specialised kernels
   std::vector<double> params;          // tape-level runtime parameters (<= HB_MAXP)
   int dyn_doubles = 0;                 // dynamic shared memory per thread (doubles) every kernel of this system is launched with
+  int rhs_cost = 0;                    // system compiler's cost model of one hamEqs evaluation
+  bool heavy = false;                  // Sys::HEAVY: one RK4 step is issue-bound, not HBM-bound (launch-shape heuristic)
   std::string source;                  // generated Sys struct
   // JIT: small systems compile all kernels in one NVRTC program at creation (cubins[K_COUNT] shared slot 0);
   // large ones compile each kernel on first use (a 12-coordinate chain takes ~10 s per kernel).
@@ -312,6 +315,19 @@ struct Scratch {
     for (auto& p : pipes) cudaGraphExecDestroy(p.exec);
     pipes.clear();
   }
+  // thread exit: a -threaded Haskell host makes HOST calls from many short-lived OS threads; give everything back
+  ~Scratch() {
+    if (device < 0) return;
+    int cur = 0;
+    if (cudaGetDevice(&cur) != cudaSuccess) { cudaGetLastError(); return; }   // (runtime already shut down at process exit)
+    cudaSetDevice(device);
+    drop_pipes();
+    for (auto e : events) cudaEventDestroy(e);
+    for (auto& st : streams) if (st) cudaStreamDestroy(st);
+    for (int i = 0; i < 3; i++) if (p[i]) cudaFree(p[i]);
+    cudaSetDevice(cur);
+    cudaGetLastError();
+  }
   void* p[3] = {nullptr, nullptr, nullptr};
   size_t cap[3] = {0, 0, 0};
   cudaStream_t stream = nullptr;      // == streams[0]
@@ -385,20 +401,14 @@ int resident_ctas(const void* fn, int block, size_t dyn_smem) {
 // first thing and griddepcontrol.wait before their first global read, so in a stream (or captured graph) of back-to-back
 // steps the next kernel's launch latency, table staging and first L2 prefetches hide under this kernel's tail.
 // The kernels index trajectories with 32 bits: callers (run_batch) hand at most HB_MAX_LAUNCH_N trajectories per launch.
-hb_status launch(const void* fn, const HbKArgs& a, long long work_items, cudaStream_t st, int block = HB_BLOCK, size_t dyn_smem = 0) {
-  if (work_items <= 0) return HB_OK;
-  static const double waves_env = [] { const char* e = std::getenv("HB_GRID_WAVES"); double t = e ? std::atof(e) : 0.0; return (t > 0 && t <= 4096) ? t : 0.0; }();
+hb_status launch(const void* fn, const HbKArgs& a, long long grid, cudaStream_t st, int block, size_t dyn_smem) {
+  if (grid <= 0) return HB_OK;
   static const bool pdl = std::getenv("HB_NO_PDL") == nullptr;
-  long long blocks = (work_items + block - 1) / block;
-  const int slots = resident_ctas(fn, block, dyn_smem);
-  if (slots < 0) return fail(HB_ERR_CUDA, "kernel needs more dynamic shared memory than the device offers");
-  const long long cap = (long long)((double)slots * (waves_env > 0 ? waves_env : 1.0));
-  if (slots > 0 && blocks > cap) blocks = cap;
-  if (blocks > 0x7fffffffLL) blocks = 0x7fffffffLL;
+  if (resident_ctas(fn, block, dyn_smem) < 0) return fail(HB_ERR_CUDA, "kernel needs more dynamic shared memory than the device offers");
+  if (grid > 0x7fffffffLL) grid = 0x7fffffffLL;
   void* args[] = {(void*)&a};
-  cudaLaunchConfig_t cfg;
-  std::memset(&cfg, 0, sizeof cfg);
-  cfg.gridDim = dim3((unsigned)blocks);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(block);
   cfg.dynamicSmemBytes = dyn_smem;
   cfg.stream = st;
@@ -411,22 +421,99 @@ hb_status launch(const void* fn, const HbKArgs& a, long long work_items, cudaStr
   return HB_OK;
 }
 
-// CTA size of a system's kernels.  HB_BLOCK is an experiment knob for small systems only (the shared-memory layouts of large
-// ones assume HB_BLOCK_OF); a size above the kernel's __launch_bounds__ (HB_BLOCK_SMALL at compile time) makes the launch
-// fail with an error, never run wrongly.
-int block_for(const hb_system* s) {
-  static const int block_env = [] { const char* e = std::getenv("HB_BLOCK"); int t = e ? std::atoi(e) : 0; return (t >= 32 && t <= 1024 && t % 32 == 0) ? t : 0; }();
-  return (block_env && s->n < HB_BIG_N) ? block_env : HB_BLOCK_OF(s->n);
-}
 // Dynamic shared memory of one launch; mirrors the layout documented at HB_DYN_DOUBLES in engine/hb_engine.cuh.
 size_t dyn_smem_bytes(const hb_system* s, int block, int in_d, int out_d, int kernel_layout) {
   size_t b = s->n >= HB_BIG_N ? (size_t)s->dyn_doubles * sizeof(double) * block : (size_t)HB_TAB_BYTES + (size_t)2 * in_d * sizeof(double) * block;
   if (kernel_layout == 2 && out_d % 2 == 0 && out_d <= HB_WSTORE_MAXD) b += (size_t)out_d * sizeof(double) * block;
   return b;
 }
-hb_status launch_sys(const hb_system* s, const void* fn, const HbKArgs& a, long long n_traj, cudaStream_t st, int in_d, int out_d) {
-  const int block = block_for(s);
-  return launch(fn, a, n_traj, st, block, dyn_smem_bytes(s, block, in_d, out_d, a.layout));
+// Launch shape of one kernel of a system: CTA size and grid.
+// Large systems: HB_BLOCK_OF threads (their shared-memory layout is compiled for it), one resident wave.
+// Small systems: the kernels are tile-scheduled (engine/hb_engine.cuh HB_KERNEL_BODY: warp w of CTA b walks tiles
+// b + G (w + W r)), so a launch is R = tiles / (resident warps) rounds long and its LAST round is only frac(R) full —
+// the few warps of a nearly empty last round run alone at latency-bound speed while the rest of the SM idles.  Measured on
+// the double pendulum, 1,048,576 trajectories, one RK4 step per launch (profiles/r2c/ab_double_pendulum.txt):
+//   5 CTAs x 128 threads / SM  (R = 11.07)  19.6 us      1 CTA x 512 (R = 13.84)  16.9 us
+//   2 CTAs x 384               (R =  9.23)  18.8 us      1 CTA x 768 (R =  9.23)  17.5 us
+// i.e. what counts is (1) few CTAs per SM — every CTA stages its own 32 KB sin/cos table image per launch — and (2) a
+// last round that is nearly full; beyond 4 warps per scheduler more resident warps buy nothing (the step is issue-bound).
+// pick_shape therefore scores every CTA size of 4..16 warps the kernel can run (occupancy queried once per kernel and
+// cached) with   waste = [frac > 0] max(0, RHO - frac x warps/SM)  +  TABLE x CTAs/SM   (in units of one tile's issue time;
+// RHO = 8: one warp alone needs ~8x its issue-bound share, TABLE = 2) and takes the cheapest, ties to more warps.
+// HB_BLOCK / HB_GRID_WAVES override (experiments).
+struct LaunchShape { int block; long long grid; };
+LaunchShape pick_shape(const hb_system* s, const void* fn, long long n_traj, int in_d, int out_d, int kernel_layout, bool heavy) {
+  static const int block_env = [] { const char* e = std::getenv("HB_BLOCK"); int t = e ? std::atoi(e) : 0; return (t >= 32 && t <= 1024 && t % 32 == 0) ? t : 0; }();
+  static const double waves_env = [] { const char* e = std::getenv("HB_GRID_WAVES"); double t = e ? std::atof(e) : 0.0; return (t > 0 && t <= 4096) ? t : 0.0; }();
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) { cudaGetLastError(); sms = 148; }
+  auto one_wave = [&](int block) -> LaunchShape {
+    const int slots = resident_ctas(fn, block, dyn_smem_bytes(s, block, in_d, out_d, kernel_layout));
+    long long blocks = (n_traj + block - 1) / block;
+    const long long cap = (long long)((double)(slots > 0 ? slots : sms) * (waves_env > 0 ? waves_env : 1.0));
+    if (blocks > cap) blocks = cap;
+    return LaunchShape{block, blocks < 1 ? 1 : blocks};
+  };
+  if (s->n >= HB_BIG_N) return one_wave(HB_BLOCK_OF(s->n));
+  if (block_env) return one_wave(block_env);
+  // HBM-bound launches (light systems, the one-evaluation kernels): what counts is bytes in flight — full occupancy, small CTAs
+  if (!heavy) return one_wave(128);
+  // CTAs per SM for every candidate size, cached per kernel
+  struct Occ { int per_sm[17]; };
+  static std::mutex mu;
+  static std::map<std::tuple<int, const void*, int, int, int>, Occ> cache;
+  const auto key = std::make_tuple(dev, fn, in_d, out_d, kernel_layout == 2 ? 1 : 0);
+  Occ occ;
+  bool have = false;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { occ = it->second; have = true; }
+  }
+  if (!have) {
+    cudaFuncAttributes fa;
+    int max_threads = 128;
+    if (cudaFuncGetAttributes(&fa, fn) == cudaSuccess) max_threads = fa.maxThreadsPerBlock; else cudaGetLastError();
+    for (int w = 0; w <= 16; w++) {
+      occ.per_sm[w] = 0;
+      if (w < 4 || 32 * w > max_threads) continue;
+      const int slots = resident_ctas(fn, 32 * w, dyn_smem_bytes(s, 32 * w, in_d, out_d, kernel_layout));
+      occ.per_sm[w] = slots > 0 ? slots / sms : 0;
+    }
+    std::lock_guard<std::mutex> lk(mu);
+    cache[key] = occ;
+  }
+  const double tiles = (double)((n_traj + 31) / 32);
+  const double RHO = 8.0, TABLE = 2.0;
+  int best_w = 4, best_c = 1, best_wsm = 0;
+  double best_cost = 1e300;
+  for (int w = 4; w <= 16; w++) {
+    for (int c = 1; c <= occ.per_sm[w]; c++) {         // c CTAs of w warps per SM
+      const int wsm = w * c;
+      if (wsm > 24) break;
+      const double R = tiles / ((double)sms * wsm);
+      const double frac = R - std::floor(R);
+      double cost = (frac > 1e-9 ? std::max(0.0, RHO - frac * wsm) : 0.0) + TABLE * c;
+      if (wsm < 12 && tiles >= (double)sms * 12) cost += 2.0 * (12 - wsm);     // too few warps to cover the FP64 latency
+      if (cost < best_cost - 1e-9 || (cost < best_cost + 1e-9 && wsm > best_wsm)) { best_cost = cost; best_w = w; best_c = c; best_wsm = wsm; }
+    }
+  }
+  if (best_wsm == 0) return one_wave(128);
+  const int block = 32 * best_w;
+  long long blocks = (n_traj + block - 1) / block;
+  const long long cap = (long long)((double)sms * best_c * (waves_env > 0 ? waves_env : 1.0));
+  if (blocks > cap) blocks = cap;
+  return LaunchShape{block, blocks < 1 ? 1 : blocks};
+}
+// heavy: is this launch issue-bound?  Stepping kernels of HEAVY systems, and any stepping kernel that takes several steps (or
+// adaptive solves: ~25 RHS each) per trajectory.
+bool heavy_launch(const hb_system* s, int kid, const HbKArgs& a) {
+  if (kid == K_STEP_RK4) return s->heavy || a.nsteps >= 4;
+  return kid == K_STEP_RKF45 || kid == K_EVOLVE_RK4 || kid == K_EVOLVE_RKF45;
+}
+hb_status launch_sys(const hb_system* s, int kid, const void* fn, const HbKArgs& a, long long n_traj, cudaStream_t st, int in_d, int out_d) {
+  const LaunchShape sh = pick_shape(s, fn, n_traj, in_d, out_d, a.layout, heavy_launch(s, kid, a));
+  return launch(fn, a, sh.grid, st, sh.block, dyn_smem_bytes(s, sh.block, in_d, out_d, a.layout));
 }
 
 void fill_params(const hb_system* s, HbKArgs& a) {
@@ -472,7 +559,7 @@ hb_status run_batch(const hb_system* sys, int kid, HbKArgs a, int64_t N, hb_mems
       CU(cudaMemcpyAsync(dts, ts, sizeof(double) * s, cudaMemcpyHostToDevice, st));   // ts is tiny; pageable copy is staged by the driver
       a.ts = dts;
     }
-    rc = launch_sys(sys, fn, a, N, st, in_d, out_d);
+    rc = launch_sys(sys, kid, fn, a, N, st, in_d, out_d);
     if (dts) cudaFreeAsync(dts, st);
     return rc;
   }
@@ -500,7 +587,8 @@ hb_status run_batch(const hb_system* sys, int kid, HbKArgs a, int64_t N, hb_mems
       if (ts) { CU(cudaMemcpyAsync(dts, ts, sizeof(double) * s, cudaMemcpyHostToDevice, st)); a.ts = (const double*)dts; }
       a.in = (const double*)din_h; a.out = (double*)dout_h; a.flags = (int*)dfl_h;
       if (a.layout == HB_LAYOUT_AOS) a.layout = 2;   // warp-transposed stores (engine/hb_engine.cuh hb_store)
-      if ((rc = launch_sys(sys, fn, a, N, st, in_d, out_d))) return rc;
+      a.host_io = 1;
+      if ((rc = launch_sys(sys, kid, fn, a, N, st, in_d, out_d))) return rc;
       CU(cudaStreamSynchronize(st));
       return HB_OK;
     }
@@ -542,9 +630,8 @@ hb_status run_batch(const hb_system* sys, int kid, HbKArgs a, int64_t N, hb_mems
   }
   cudaStream_t s_up = g_scratch.streams[0], s_k = g_scratch.streams[1], s_down = g_scratch.streams[2];
   if ((rc = g_scratch.need_events((int)(2 * chunks) + 1))) return rc;
-  const int blk = block_for(sys);
-  if (resident_ctas(fn, blk, dyn_smem_bytes(sys, blk, in_d, out_d, hybrid ? 2 : a.layout)) < 0)   // (also keeps this query out of a capture)
-    return fail(HB_ERR_CUDA, "kernel needs more dynamic shared memory than the device offers");
+  (void)pick_shape(sys, fn, N, in_d, out_d, hybrid ? 2 : a.layout, heavy_launch(sys, kid, a));   // (keeps the occupancy queries out of a capture)
+  (void)pick_shape(sys, fn, (N + chunks - 1) / chunks, in_d, out_d, hybrid ? 2 : a.layout, heavy_launch(sys, kid, a));
   auto enqueue = [&]() -> hb_status {
     if (ts) {
       double* dts = (double*)((char*)din + in_bytes);
@@ -575,7 +662,7 @@ hb_status run_batch(const hb_system* sys, int kid, HbKArgs a, int64_t N, hb_mems
         ac.flags = flags ? (int*)dfl_h + i0 : nullptr;   // read-modify-write in host memory, only for flagged trajectories
         ac.layout = 2;
       }
-      hb_status lrc = launch_sys(sys, fn, ac, chunks == 1 ? N : n, s_k, in_d, out_d);
+      hb_status lrc = launch_sys(sys, kid, fn, ac, chunks == 1 ? N : n, s_k, in_d, out_d);
       if (lrc) return lrc;
       if (hybrid) { if (c + 1 == chunks) { CU(cudaEventRecord(done, s_k)); CU(cudaStreamWaitEvent(s_down, done, 0)); } continue; }
       CU(cudaEventRecord(done, s_k));
@@ -637,6 +724,9 @@ bool bad_layout(hb_layout l) { return l != HB_LAYOUT_AOS && l != HB_LAYOUT_SOA; 
 // ================================================================================ C ABI ======
 extern "C" {
 
+// internal (ensemble.cpp): sets the calling thread's error message
+hb_status hb_internal_fail(hb_status s, const char* msg) { return fail(s, msg ? msg : ""); }
+
 int32_t hb_abi_version(void) { return HB_ABI_VERSION; }
 const char* hb_last_error(void) { return g_err.c_str(); }
 
@@ -675,7 +765,7 @@ hb_status hb_system_builtin(hb_builtin id, const double* params, int32_t n_param
   if (hb_aot_kargs_size() != sizeof(HbKArgs)) { delete s; return fail(HB_ERR_INVALID, "internal: host/device HbKArgs layout mismatch"); }
   hb::GeneratedSystem g;
   std::string err;
-  if (hb::generate_system(spec, std::string("HbSys_") + hb::builtin_name(id) + (s->baked ? "_dflt" : ""), g, err)) s->source = g.source;
+  if (hb::generate_system(spec, std::string("HbSys_") + hb::builtin_name(id) + (s->baked ? "_dflt" : ""), g, err)) { s->source = g.source; s->rhs_cost = g.rhs_cost; s->heavy = g.heavy; }
   *out = s;
   return HB_OK;
 }
@@ -704,6 +794,8 @@ hb_status hb_system_from_tape(int32_t m, int32_t n, const double* inertia, const
   s->m = m; s->n = n; s->builtin = -1;
   s->params.assign(params, params + n_params);
   s->source = g.source;
+  s->rhs_cost = g.rhs_cost;
+  s->heavy = g.heavy;
   s->gen = g;
   s->dyn_doubles = HB_DYN_DOUBLES(n, g.ne);
   s->arch = jit_arch();
@@ -772,6 +864,8 @@ hb_status hb_batch_evolve(const hb_system* sys, hb_integrator integ, int32_t rk4
   if (!ts || s < 2) return fail(HB_ERR_INVALID, "evolveHam needs at least two grid times (2 <= s, src/Numeric/Hamilton.hs:435)");
   for (int k = 1; k < s; k++) if (!(ts[k] >= ts[k - 1])) return fail(HB_ERR_INVALID, "time grid must be non-decreasing");
   if (integ == HB_INTEG_RK4 && rk4_substeps < 1) return fail(HB_ERR_INVALID, "rk4_substeps must be >= 1");
+  // the reference's initial step is (ts[1] - ts[0]) / 100 (src/Numeric/Hamilton.hs:447): zero makes its solver spin forever
+  if (integ == HB_INTEG_RKF45_GSL && !(ts[1] > ts[0])) return fail(HB_ERR_INVALID, "RKF45_GSL needs ts[1] > ts[0]: the initial step size is (ts[1] - ts[0]) / 100");
   HbKArgs a; fill_params(sys, a); a.layout = layout; a.s = s; a.substeps = rk4_substeps;
   return run_batch(sys, integ == HB_INTEG_RK4 ? K_EVOLVE_RK4 : K_EVOLVE_RKF45, a, N, mem, y0, 2 * sys->n, out, 2 * sys->n, s, flags, ts,
                    s, stream);
@@ -816,7 +910,10 @@ hb_status hb_batch_init_random(const hb_system* sys, uint64_t seed, int64_t firs
   HbKArgs a; std::memset(&a, 0, sizeof a);
   a.out = y_device; a.N = N; a.nsteps = D; a.layout = layout; a.seed = seed; a.first = first;
   for (int c = 0; c < D; c++) { a.prm[c] = lo[c]; a.prm[D + c] = hi[c]; }
-  return launch(hb_aot_init_random(), a, N * D, (cudaStream_t)stream);
+  long long grid = (N * D + HB_BLOCK - 1) / HB_BLOCK;
+  const int slots = resident_ctas(hb_aot_init_random(), HB_BLOCK, 0);
+  if (slots > 0 && grid > 2LL * slots) grid = 2LL * slots;
+  return launch(hb_aot_init_random(), a, grid, (cudaStream_t)stream, HB_BLOCK, 0);
 }
 
 // ---- single-trajectory mirrors ---------------------------------------------------------------

@@ -456,6 +456,16 @@ bool generate_system(const SystemSpec& spec, const std::string& name, GeneratedS
   bool trig = false;
   for (const Node& nd : G.nodes) trig = trig || nd.op == Op::Sin || nd.op == Op::Cos;
   os << "  static constexpr bool TRIG = " << (trig ? "true" : "false") << ";\n";
+  // HEAVY: is one RK4 step of a trajectory issue-bound or HBM-bound?  Issue clocks per tile of 32 trajectories and SM:
+  // (2 clk x (4 RHS x (cost model + solve) + 14 n of RK4 algebra) + 60 of bookkeeping) / 4 schedulers; HBM clocks per tile and
+  // SM: 32 x 32 n bytes / 22.4 bytes per clock (6.5 TB/s over 148 SMs at 1.965 GHz).  Issue-bound systems stage their next
+  // Phase with cp.async and run one CTA per SM; HBM-bound ones keep plain loads, an L2 prefetch two tiles ahead and full
+  // occupancy (cp.async costs them 30-50 %: profiles/r2e).
+  const double solve_cost = n * n * n / 6.0 + n * n + 5.0 * n;
+  const double rhs_cost = SH.ok ? SH.cost_sym : SH.cost_direct;
+  const double issue_clk = (2.0 * (4.0 * (rhs_cost + solve_cost) + 14.0 * n) + 60.0) / 4.0, hbm_clk = 32.0 * 32.0 * n / 22.4;
+  const bool heavy = issue_clk >= 1.5 * hbm_clk;
+  os << "  static constexpr bool HEAVY = " << (heavy ? "true" : "false") << ";   // issue " << (int)issue_clk << " vs HBM " << (int)hbm_clk << " clocks per tile\n";
   os << table_fn("jidx", "int i, int j", "i * N + j", jidx);
   os << table_fn("jrow", "int e", "e", jrow) << table_fn("jcol", "int e", "e", jcol);
   os << table_fn("hrow", "int e", "e", hrow) << table_fn("hj", "int e", "e", hj) << table_fn("hk", "int e", "e", hk);
@@ -523,6 +533,8 @@ bool generate_system(const SystemSpec& spec, const std::string& name, GeneratedS
   out.m = m; out.n = n; out.nj = NJ; out.nh = NH;
   out.n_nodes = (int)G.nodes.size();
   out.ne = SH.ok ? (int)SH.carried.size() : 0;
+  out.rhs_cost = SH.ok ? SH.cost_sym : SH.cost_direct;
+  out.heavy = heavy;
   return true;
 }
 

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define HB_ABI_VERSION 1
+#define HB_ABI_VERSION 2
 #define HB_MAX_N 16      /* generalized coordinates per system            */
 #define HB_MAX_M 48      /* Cartesian coordinates per system              */
 #define HB_MAX_PARAMS 32 /* runtime parameters (HB_OP_PARAM leaves)       */
@@ -199,6 +199,41 @@ hb_status hb_batch_underlying_pos(const hb_system* sys, int64_t N, hb_layout lay
 hb_status hb_batch_init_random(const hb_system* sys, uint64_t seed, int64_t first, int64_t N,
                                hb_layout layout, const double* lo, const double* hi /* 2n each, host */,
                                double* y_device, void* stream);
+
+/* ---- multi-GPU ensembles ----------------------------------------------------
+ * Trajectories are independent (stepHam is a pure function of each Phase, src/Numeric/Hamilton.hs:390-399), so an
+ * ensemble of N initial conditions is block-split over the GPUs of THIS process: device g of `ndev` owns trajectories
+ * [g*N/ndev, (g+1)*N/ndev) in its own memory (array of Phases), steps them with no communication, and ONE NCCL
+ * all-gather over NVLink assembles the final Phases on every device.  Single process, one host thread per device inside
+ * every call (a Haskell host links with -threaded, hamilton.cabal:54; no MPI / torchrun needed).
+ * All calls are blocking unless stated; the ensemble may be used from any one thread at a time. */
+typedef struct hb_ensemble hb_ensemble;
+
+/* devices: ndev CUDA device ordinals, or NULL for 0..ndev-1.  Allocates the shards (two N/ndev x 2n buffers per device
+ * that swap roles every launch), one stream per device and the NCCL communicators (ncclCommInitAll).
+ * HB_ERR_UNSUPPORTED when libnccl cannot be loaded and ndev > 1. */
+hb_status hb_ensemble_create(const hb_system* sys, int32_t ndev, const int32_t* devices, int64_t N, hb_ensemble** out);
+void hb_ensemble_free(hb_ensemble* ens);
+hb_status hb_ensemble_dims(const hb_ensemble* ens, int32_t* ndev, int64_t* N, int64_t* first /* ndev+1 shard offsets, may be NULL */);
+
+/* Initial Phases: generated on every device from the counter-based RNG of hb_batch_init_random with GLOBAL trajectory
+ * indices (no scatter), or uploaded from one host array of N Phases (array of Phases). */
+hb_status hb_ensemble_init_random(hb_ensemble* ens, uint64_t seed, const double* lo, const double* hi /* 2n each */);
+hb_status hb_ensemble_upload(hb_ensemble* ens, const double* y_host /* N x 2n */);
+
+/* `launches` x hb_batch_step(integ, dt, nsteps) on every shard concurrently (state read from and written to HBM every
+ * launch).  Returns when every device has finished; *gpu_ms (may be NULL) = device time, max over devices. */
+hb_status hb_ensemble_step(hb_ensemble* ens, hb_integrator integ, double dt, int32_t nsteps, int32_t launches, double* gpu_ms);
+
+/* One ncclAllGather of the current Phases: afterwards EVERY device holds all N Phases (hb_ensemble_gathered gives the
+ * device pointers); y_host (may be NULL) additionally receives them from device 0.  *gpu_ms = device time of the
+ * collective, max over devices.  The first call allocates and registers (ncclCommRegister) the N x 2n receive buffers. */
+hb_status hb_ensemble_gather(hb_ensemble* ens, double* y_host /* N x 2n or NULL */, double* gpu_ms);
+/* Device pointers: the shard of device index g (Ng x 2n, current state) / its gathered copy (N x 2n, valid after gather). */
+hb_status hb_ensemble_shard(const hb_ensemble* ens, int32_t g, double** y_device, int64_t* n_shard);
+hb_status hb_ensemble_gathered(const hb_ensemble* ens, int32_t g, double** y_device);
+/* Per-trajectory HB_FLAG_* bits accumulated since creation, all N, to host. */
+hb_status hb_ensemble_flags(hb_ensemble* ens, int32_t* flags_host /* N */);
 
 /* ---- single-trajectory mirrors of the Haskell API (host pointers, run on the GPU with N = 1).
  * A numerical failure returns HB_ERR_NUMERIC, the analogue of the reference's `error`. -------- */

@@ -7,16 +7,7 @@ a graph of K launches ping-ponging between two buffers (a real stepping loop: L2
 import os, subprocess, sys
 VARIANTS = [
     ("default", {}),
-    ("r2a build: register ping-pong prefetch", {"HB_LIB_PATH": "profiles/ab_libs/lib_r2a_pingpong.so"}),
-    ("default (again)", {}),
-    ("no cp.async staging (plain loads)", {"HB_JIT_DEFINES": "HB_ASYNC_STAGE=0"}),
-    ("2 waves", {"HB_GRID_WAVES": "2"}),
-    ("CTA 256 (6 warps/scheduler)", {"HB_JIT_DEFINES": "HB_BLOCK_SMALL=256", "HB_BLOCK": "256"}),
-    ("CTA 384 (6 warps/scheduler)", {"HB_JIT_DEFINES": "HB_BLOCK_SMALL=384", "HB_BLOCK": "384"}),
-    ("CTA 192", {"HB_JIT_DEFINES": "HB_BLOCK_SMALL=192", "HB_BLOCK": "192"}),
-    ("CTA 256, 2 waves", {"HB_JIT_DEFINES": "HB_BLOCK_SMALL=256", "HB_BLOCK": "256", "HB_GRID_WAVES": "2"}),
-    ("no L2 prefetch before the wait", {"HB_JIT_DEFINES": "HB_PRE_L2=0"}),
-    ("no PDL", {"HB_NO_PDL": "1"}),
+    ("round-1 final build", {"HB_LIB_PATH": "profiles/ab_libs/lib_r1_final.so"}),
 ]
 def worker(name, log2n):
     sys.path.insert(0, ".")
@@ -55,8 +46,19 @@ def worker(name, log2n):
     t_ring = timed(g_ring.replay) / K
     t_chain = timed(g_chain.replay) / K
     t_16 = timed(lambda: [s.batch_step(ins[i % ring], 0.01, 16, out=outs[i % ring]) for i in range(8)]) / 8
-    print("RESULT ring %.3f us/launch (%.3e steps/s)  chain %.3f us/launch (%.3e)  fused16 %.3e steps/s" %
-          (t_ring * 1e3, N / t_ring * 1e3, t_chain * 1e3, N / t_chain * 1e3, N * 16 / t_16 * 1e3))
+    # e2e: the same call on pinned HOST arrays (blocking), as bench.py's e2e leg
+    import time
+    src = ins[0].cpu()
+    h_in = [src.clone().pin_memory() for _ in range(2)]
+    h_out = [torch.empty_like(src).pin_memory() for _ in range(2)]
+    for i in range(3): s.batch_step(h_in[i % 2], 0.01, 1, out=h_out[i % 2])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(20): s.batch_step(h_in[i % 2], 0.01, 1, out=h_out[i % 2])
+    torch.cuda.synchronize()
+    t_e2e = (time.perf_counter() - t0) / 20
+    print("RESULT ring %.3f us/launch (%.3e steps/s)  chain %.3f us  fused16 %.3e  e2e %.3f ms/call (%.3e steps/s)" %
+          (t_ring * 1e3, N / t_ring * 1e3, t_chain * 1e3, N * 16 / t_16 * 1e3, t_e2e * 1e3, N / t_e2e))
 if sys.argv[1] == "run":
     worker(sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 20)
 else:

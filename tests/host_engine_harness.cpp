@@ -48,7 +48,7 @@ static constexpr int N = S::N, D = 2 * S::N;
 
 static HbCtx ctx() { HbCtx cx; cx.tab_s = 0; hb_ctx_reset(cx); return cx; }
 // HB_FLAG_* bits (integrator flags + deferred pivot test) | "left the fast domain" << 8
-static int result(const HbCtx& cx, int flag) { return hb_ctx_flags(cx, flag) | (cx.oob ? 1 << 8 : 0); }
+static int result(const HbCtx& cx, int flag) { return hb_ctx_flags(cx, flag) | (cx.oob ? 1 << 8 : 0); }   // (a failed pivot test alone also means "retry out of line": hb_retry)
 
 extern "C" void dims(int* o) { o[0] = S::M; o[1] = S::N; o[2] = S::SYMH ? 1 : 0; o[3] = N >= HB_BIG_N ? 1 : 0; }
 
@@ -132,7 +132,7 @@ template <int NN> static int spd(const double* A_packed, const double* b, double
   double A[NN * (NN + 1) / 2];
   for (int i = 0; i < NN * (NN + 1) / 2; i++) A[i] = A_packed[i];
   int minpiv = 0x7fffffff;
-  hb_spd_solve<NN>(A, b, x, minpiv);
+  hb_spd_solve<NN, true>(A, b, x, minpiv);
   return minpiv < 0x00100000 ? HB_FLAG_NOT_SPD : 0;
 }
 extern "C" int spd_solve(int n, const double* A_packed, const double* b, double* x) {

@@ -23,7 +23,7 @@ NAMES = list(BOXES)
 
 def test_abi_library_exports_every_declared_symbol():
     lib = L.lib()
-    assert lib.hb_abi_version() == 1
+    assert lib.hb_abi_version() == 2
     hdr = open(os.path.join(ROOT, "include", "hamilton_b200.h")).read()
     declared = set(re.findall(r"\b(hb_[a-z0-9_]+)\s*\(", hdr))
     declared -= {"hb_op", "hb_tape", "hb_status"}
@@ -44,6 +44,8 @@ def test_no_cpu_fallback_without_device():
         s.batch_step(np.zeros((4, 4)), 0.01)
     n = C.c_int32(-1)
     assert L.lib().hb_device_count(C.byref(n)) == L.ERR_NO_DEVICE and n.value == 0
+    with pytest.raises(hb.NoDeviceError):
+        hb.ensemble.Ensemble(s, 1024, 1)
 
 
 def _host_eval(system, name, tmp):
@@ -355,3 +357,74 @@ def test_symbolic_ham_eqs_on_random_user_maps(m, n, seed, force, oracle_mod):
             checked += 1
         if force:
             assert checked > 0 or "hamEqs form: direct" in g.source()
+
+
+def test_haskell_shim_matches_header():
+    """haskell/Numeric/Hamilton/B200.hs cannot be compiled here (no GHC): check what can be checked statically — every
+    `foreign import` names a function of include/hamilton_b200.h with the same arity and argument kinds, nothing is left
+    `undefined`, and every name of the reference's export list (src/Numeric/Hamilton.hs:28-70) is defined."""
+    hs = open(os.path.join(ROOT, "haskell", "Numeric", "Hamilton", "B200.hs")).read()
+    hdr = open(os.path.join(ROOT, "include", "hamilton_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", " ", hdr, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b([A-Za-z_][A-Za-z0-9_ *]*?[ *])(hb_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr):
+        ret, name, args = m.group(1).strip(), m.group(2), m.group(3).strip()
+        kinds = []
+        for a in ([] if args in ("", "void") else args.split(",")):
+            a = a.strip()
+            if "*" in a:
+                kinds.append("ptr")
+            elif re.match(r"(const\s+)?double\b", a):
+                kinds.append("double")
+            elif re.match(r"(const\s+)?(int64_t)\b", a):
+                kinds.append("i64")
+            elif re.match(r"(const\s+)?(uint64_t)\b", a):
+                kinds.append("u64")
+            elif re.match(r"(const\s+)?(int32_t|hb_integrator|hb_layout|hb_memspace|hb_builtin|hb_status)\b", a):
+                kinds.append("i32")
+            elif re.match(r"size_t\b", a):
+                kinds.append("size")
+            else:
+                raise AssertionError("unparsed C parameter %r of %s" % (a, name))
+        protos[name] = (ret, kinds)
+    hs_kind = {"Int32": "i32", "Int64": "i64", "Word64": "u64", "Double": "double"}
+    imports = re.findall(r'foreign import ccall safe "(&?)(hb_[a-z0-9_]+)"\s*\n?\s*\w+ ::\s*([^\n]*)', hs)
+    assert len(imports) >= 24
+    for amp, name, sig in imports:
+        assert name in protos, name
+        sig = sig.split("--")[0].strip()
+        if amp:                                   # address of a finaliser: FunPtr (Ptr X -> IO ())
+            assert sig.startswith("FunPtr") and protos[name][1] == ["ptr"], name
+            continue
+        parts = [x.strip() for x in re.split(r"->(?![^()]*\))", sig)]
+        res, params = parts[-1], parts[:-1]
+        got = ["ptr" if x.startswith("Ptr") or x.startswith("(Ptr") else hs_kind[x] for x in params]
+        assert got == protos[name][1], (name, got, protos[name][1])
+        assert res in ("IO Int32", "IO CString"), (name, res)
+    assert not re.search(r"=\s*undefined\b", hs) and "undefined;" not in hs
+    for name in ("mkSystem", "mkSystem'", "underlyingPos", "toPhase", "fromPhase", "momenta", "velocities", "keC", "keP", "pe", "lagrangian",
+                 "hamiltonian", "hamEqs", "stepHam", "evolveHam", "evolveHam'", "stepHamC", "evolveHamC", "evolveHamC'", "batchStep", "batchEvolve"):
+        assert re.search(r"^" + re.escape(name) + r"\s*(::|\n\s+::)", hs, flags=re.M), name
+        assert re.search(r"^" + re.escape(name) + r"\s[^:\n]*=", hs, flags=re.M), name
+    for inst in ("Num", "Fractional", "Floating", "Eq", "Ord", "Real", "RealFrac", "RealFloat"):
+        assert "instance %s Tr where" % inst in hs, inst
+
+
+def test_python_mirror_rejects_buffers_the_c_library_would_overrun():
+    """dtype and shape of every caller-supplied buffer are validated before the pointer reaches the C ABI."""
+    s = hb.systems.builtin(hb.systems.DOUBLE_PENDULUM)
+    y = np.zeros((8, 4))
+    with pytest.raises(ValueError):
+        s.batch_step(y.astype(np.int32), 0.01)                      # int32 data read as doubles: twice its size
+    with pytest.raises(ValueError):
+        s.batch_step(y, 0.01, out=np.zeros((4, 4)))                 # too small an output
+    with pytest.raises(ValueError):
+        s.batch_step(y, 0.01, out=np.zeros((8, 4), dtype=np.float32))
+    with pytest.raises(ValueError):
+        s.batch_step(y, 0.01, flags=np.zeros(8, dtype=np.int64))
+    with pytest.raises(ValueError):
+        s.batch_step(y, 0.01, flags=np.zeros(4, dtype=np.int32))
+    with pytest.raises(ValueError):
+        s.batch_energies(y, out=np.zeros((8, 3)))
+    with pytest.raises(ValueError):
+        s.batch_evolve(y, [0.0, 0.1, 0.2], out=np.zeros((2, 8, 4)))
