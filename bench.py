@@ -7,8 +7,9 @@ the I/O-honest mode SURVEY.md §8(d) defines (32·n algorithmic bytes per trajec
 describe the same launches.  Batches rotate through a ring of buffers larger than L2 (see config.l2).
 
 Headline workload (N = 1 and the per-GPU shard at N > 1): BASELINE configs[1] — double pendulum (System 4 2), batch
-1,048,576 random initial Phases per GPU.  The K launches are captured into one CUDA graph; the graph is replayed R times so
-that the timed region is at least 100 ms (ms_per_step = region / (K·R)).
+1,048,576 random initial Phases per GPU.  K (--steps) launches estimate the rate; the timed region is ONE replay of a CUDA graph of
+L = K * ceil(100 ms / (K launches)) launches (ms_per_step = region / L) — long enough for the clock sampler, and free of the
+gaps between consecutive replays of one executable graph, which are launch plumbing.
 
   value      steps/s with the batch resident in HBM (device pointers through the C ABI), CUDA-event timed, max over ranks.
   e2e        the same call through the C ABI with HOST buffers (pinned): H2D + kernel + D2H inside the timed region;
@@ -49,6 +50,7 @@ DT = 0.01
 SEED = 0x48414D49
 METRIC = "phase-space RK4 steps/sec (batched trajectories)"
 MIN_REGION_MS = 100.0
+NVML_POLL_S = float(os.environ.get("HB_BENCH_NVML_MS", "10")) * 1e-3   # ~10 clock samples per 100 ms timed region
 # name -> (builtin id, n, lo, hi): sampling boxes of SURVEY.md §8(d)
 SYS = {
     "pendulum": (0, 1, [-PI, -1.0], [PI, 1.0]),
@@ -69,7 +71,7 @@ def peaks():
 
 
 class ClockSampler:
-    """SM clock and throttle reasons DURING the timed region: NVML polled from a thread every ~1 ms, started well before the
+    """SM clock and throttle reasons DURING the timed region: NVML polled from a thread every ~10 ms, started well before the
     region (falls back to `nvidia-smi -lms 20`)."""
 
     REASONS = (("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40), ("sw_power_cap", 0x4))
@@ -116,7 +118,7 @@ class ClockSampler:
                 self.rows.append((time.time(), clk, mask))
             except Exception:
                 pass
-            time.sleep(0.0005)
+            time.sleep(NVML_POLL_S)
 
     def _read(self):
         for line in self.proc.stdout:
@@ -148,7 +150,7 @@ class ClockSampler:
                     reasons.add(name)
         sm = [c for c, _m in inside]
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.mx, "reasons": sorted(reasons), "samples": len(sm),
-                "sampled": ("NVML every ~1 ms, " if self.h is not None else "nvidia-smi -lms 20, ") + where}
+                "sampled": ("NVML every ~10 ms, " if self.h is not None else "nvidia-smi -lms 20, ") + where}
 
 
 def bind_near_gpu(index):
@@ -256,32 +258,39 @@ class Harness:
             sys.stderr.write("bench: CUDA-graph capture failed (%r); timing eager launches\n" % (ex,))
             return (lambda: [f() for f in launches]), "eager"
 
-    def time_replays(self, replay, K, warm_replays=1, sampler=None):
-        """Returns (ms per launch, replays, clocks).  The region is exactly R replays of the K-launch graph."""
+    def time_launches(self, launch, K, sampler=None):
+        """launch(i) enqueues the i-th launch on the current stream.  Times L = K * ceil(100 ms / (K launches)) launches
+        captured in ONE CUDA graph and replayed ONCE: consecutive replays of the same executable graph do not overlap (the
+        second waits for the first and pays the graph's submission again — measured 1.3 us per kernel node,
+        profiles/r2i/ab_graph_size.txt), which is launch plumbing, not the kernel.  Returns (ms per launch, L, region ms,
+        clocks, how)."""
         torch = self.torch
-        for _ in range(warm_replays):
-            replay()
-        self.barrier()
+        small, how = self.capture([(lambda i=i: launch(i)) for i in range(K)])
+        small(); self.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); replay(); e1.record()
+        e0.record(); small(); e1.record()
         self.barrier()
         est = max(e0.elapsed_time(e1), 1e-3)
         R = max(1, int(math.ceil(MIN_REGION_MS / est)))
-        if self.world > 1:   # every rank replays the same number of times
+        if self.world > 1:   # every rank times the same number of launches
             t = torch.tensor([R], dtype=torch.int64, device=self.dev)
             self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
             R = int(t.item())
+        L = K * R
+        if R > 1:
+            del small
+            big, how = self.capture([(lambda i=i: launch(i)) for i in range(L)])
+        else:
+            big = small
+        big()                                                    # warm: uploads the graph
         self.barrier()
         t0 = time.time()
-        e0.record()
-        for _ in range(R):
-            replay()
-        e1.record()
+        e0.record(); big(); e1.record()
         self.barrier()
         t1 = time.time()
         ms = e0.elapsed_time(e1)
         clocks = sampler.stop(t0, t1) if sampler is not None else None
-        return ms / (K * R), R, ms, clocks
+        return ms / L, L, ms, clocks, how
 
     def reduce_max(self, x):
         if self.world == 1:
@@ -307,11 +316,10 @@ def bench_simple(H, name, N, K, kernel):
     L = H.L
     for i in range(3):
         s.batch_step(ins[i % ring], DT, 1, integ=L.RK4, out=outs[i % ring])
-    replay, how = H.capture([(lambda i=i: s.batch_step(ins[i % ring], DT, 1, integ=L.RK4, out=outs[i % ring])) for i in range(K)])
-    per, R, _ms, _ = H.time_replays(replay, K)
+    per, nl, _ms, _, how = H.time_launches(lambda i: s.batch_step(ins[i % ring], DT, 1, integ=L.RK4, out=outs[i % ring]), K)
     per = H.reduce_max(per)
     return {"workload": "%s (System %d %d), batch %d, RK4 dt=0.01, one step per launch" % (name, 2 * n, n, N), "value": N / (per * 1e-3),
-            "unit": "steps/s", "ms_per_step": per, "launches_timed": K * R, "launch": how,
+            "unit": "steps/s", "ms_per_step": per, "launches_timed": nl, "launch": how,
             "l2": "ring of %d (in,out) pairs = %d MiB" % (ring, ring * 2 * N * 2 * n * 8 >> 20), "roofline": roofline_obj(n, N, per, kernel)}
 
 
@@ -333,13 +341,12 @@ def bench_config3(H, K):
         cur.wait_stream(s1); cur.wait_stream(s2)
     for i in range(3):
         step(i)
-    replay, how = H.capture([(lambda i=i: step(i)) for i in range(K)])
-    per, R, _ms, _ = H.time_replays(replay, K)
+    per, nl, _ms, _, how = H.time_launches(step, K)
     algo = Np * 32 + Np * 64
     peak, peak_src = peaks()
     ach = algo / (per * 1e-3) / 1e9
     return {"workload": "2,097,152 pendulums (System 2 1) + 2,097,152 two-body orbits (System 4 2), mixed batch 4,194,304, two streams (BASELINE configs[2])",
-            "value": 2 * Np / (per * 1e-3), "unit": "steps/s", "ms_per_step": per, "launches_timed": 2 * K * R, "launch": how,
+            "value": 2 * Np / (per * 1e-3), "unit": "steps/s", "ms_per_step": per, "launches_timed": 2 * nl, "launch": how,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
                          "kernel": "hbk_pendulum_step_rk4 + hbk_two_body_dflt_step_rk4 (concurrent)", "algorithmic_bytes_per_launch": algo}}
 
@@ -358,7 +365,7 @@ def bench_config4(H, steps=1000):
     bufs = [a, b]
     for i in range(4):
         s.batch_step(bufs[i % 2], DT, 1, integ=L.RK4, out=bufs[(i + 1) % 2])
-    K = 100                                                  # the graph holds 100 launches; steps / 100 replays
+    K = steps                                                # ONE graph of all the launches (no gaps between replays)
     replay, how = H.capture([(lambda i=i: s.batch_step(bufs[i % 2], DT, 1, integ=L.RK4, out=bufs[(i + 1) % 2])) for i in range(K)])
     if world > 1:
         for _ in range(2):                                   # warm the communicator and its buffer registration
@@ -453,8 +460,7 @@ def main():
     for i in range(args.warmup):
         step(i)
     H.barrier()
-    replay, how = H.capture([(lambda i=i: step(i)) for i in range(K)])
-    launch_ms, R, region_ms, clocks = H.time_replays(replay, K, sampler=sampler)
+    launch_ms, n_launches, region_ms, clocks, how = H.time_launches(step, K, sampler=sampler)
     assert int(flags.sum().item()) == 0, "numerical failure flags raised during the bench"
 
     # explanation only: the same kernel with 16 RK4 steps fused per launch (state stays in registers between steps)
@@ -468,8 +474,7 @@ def main():
     fused_value = world * N * 16 * 8 / (f0.elapsed_time(f1) * 1e-3)
     # explanation only: a real stepping loop (each launch reads what the previous one wrote: L2-resident 32 MiB state)
     ca, cb = ring_in[0].clone(), ring_out[0]
-    chain, _ = H.capture([(lambda i=i: sysm.batch_step(ca if i % 2 == 0 else cb, DT, 1, integ=L.RK4, out=cb if i % 2 == 0 else ca)) for i in range(K)])
-    chain_ms, _, _, _ = H.time_replays(chain, K)
+    chain_ms, _, _, _, _ = H.time_launches(lambda i: sysm.batch_step(ca if i % 2 == 0 else cb, DT, 1, integ=L.RK4, out=cb if i % 2 == 0 else ca), K)
 
     # ---------------- final collection: one NCCL all-gather of the final Phases ----------------
     gather_ms = 0.0
@@ -532,7 +537,7 @@ def main():
     launch_ms, gather_ms, chain_ms = [float(x) for x in times.tolist()]
 
     if rank == 0:
-        total_steps = world * N * K * R
+        total_steps = world * N * n_launches
         value = world * N / (launch_ms * 1e-3)
         roof = roofline_obj(2, N, launch_ms, "hbk_double_pendulum_dflt_step_rk4")
         try:
@@ -567,10 +572,11 @@ def main():
             "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
             "ms_per_step": launch_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": main_config(world, {"launch": how, "graph_replays": R, "timed_region_ms": region_ms, "launches_timed": K * R,
+            "config": main_config(world, {"launch": how, "timed_region_ms": region_ms, "launches_timed": n_launches,
+                                          "timing": "K = --steps launches estimate the rate; launches_timed = K * ceil(100 ms / that) launches captured in ONE graph, replayed once warm and once timed",
                                           "l2": "inputs larger than L2: ring of %d (in,out) batch pairs = %d MiB touched per cycle" % (RING, RING * 64)}),
             "clocks": clocks,
-            "gpu_launches": K * R,
+            "gpu_launches": n_launches,
             "e2e": {"value": world * N * e2e_calls / (e2e_ms * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": N * 32, "d2h_bytes_per_step": N * 32,
                     "steps": e2e_calls, "call": "hb_batch_step(HB_INTEG_RK4, nsteps=1, HB_MEM_HOST) on pinned host arrays, blocking: one kernel reads the Phases from and writes the results to host memory over PCIe (DESIGN.md section 2)",
                     "host_binding": numa, "by_nsteps": by_nsteps},
@@ -582,7 +588,7 @@ def main():
         }
         if world > 1:
             out["gather_ms"] = gather_ms
-            out["value_with_gather"] = total_steps / ((launch_ms * K * R + gather_ms) * 1e-3)
+            out["value_with_gather"] = total_steps / ((launch_ms * n_launches + gather_ms) * 1e-3)
         if cpu_v is not None:
             out["cpu_baseline"] = {"value": cpu_v, "unit": "steps/s", "cores": cpu_threads, "kind": "port",
                                    "sample": "all %(trajectories)d trajectories x %(rk4_steps_each)d RK4 steps in %(seconds)s s (oracle/hamilton_oracle.c, pthreads)" % cpu_sample}

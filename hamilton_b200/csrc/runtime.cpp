@@ -372,13 +372,27 @@ struct Scratch {
 thread_local Scratch g_scratch;
 
 // Resident CTA slots of a kernel on the current device (SMs x occupancy), cached per (device, function).
+// Per-kernel caches, keyed by the kernel handle.  Handles of NVRTC-compiled systems are reused by the driver after
+// hb_system_free (cudaLibraryUnload), so freeing a system purges its entries (forget_kernel) — a stale "opt-in shared memory
+// already granted" entry makes the next kernel at that address fail to launch.
+struct ShapeOcc { int per_sm[17]; };
+std::mutex g_kcache_mu;
+std::map<std::tuple<int, const void*, int, size_t>, int> g_occ_cache;                   // (device, kernel, block, dyn smem) -> resident CTAs
+std::map<std::pair<int, const void*>, size_t> g_granted_dyn;                            // opt-in dynamic shared memory granted per kernel
+std::map<std::tuple<int, const void*, int, int, int>, ShapeOcc> g_shape_cache;          // pick_shape: CTAs per SM per candidate size
+void forget_kernel(const void* fn) {
+  std::lock_guard<std::mutex> lk(g_kcache_mu);
+  for (auto it = g_occ_cache.begin(); it != g_occ_cache.end();) it = std::get<1>(it->first) == fn ? g_occ_cache.erase(it) : std::next(it);
+  for (auto it = g_granted_dyn.begin(); it != g_granted_dyn.end();) it = it->first.second == fn ? g_granted_dyn.erase(it) : std::next(it);
+  for (auto it = g_shape_cache.begin(); it != g_shape_cache.end();) it = std::get<1>(it->first) == fn ? g_shape_cache.erase(it) : std::next(it);
+}
+
 int resident_ctas(const void* fn, int block, size_t dyn_smem) {
-  static std::mutex mu;
-  static std::map<std::tuple<int, const void*, int, size_t>, int> cache;
-  static std::map<std::pair<int, const void*>, size_t> max_dyn;   // opt-in dynamic shared memory already granted per function
+  auto& cache = g_occ_cache;
+  auto& max_dyn = g_granted_dyn;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;
-  std::lock_guard<std::mutex> lk(mu);
+  std::lock_guard<std::mutex> lk(g_kcache_mu);
   auto it = cache.find(std::make_tuple(dev, fn, block, dyn_smem));
   if (it != cache.end()) return it->second;
   int sms = 0, per_sm = 0;
@@ -417,7 +431,17 @@ hb_status launch(const void* fn, const HbKArgs& a, long long grid, cudaStream_t 
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  CU(cudaLaunchKernelExC(&cfg, fn, args));
+  cudaError_t le = cudaLaunchKernelExC(&cfg, fn, args);
+  if (le != cudaSuccess) {   // say what was asked for: a launch failure is otherwise undiagnosable from the status alone
+    cudaGetLastError();
+    cudaFuncAttributes fa;
+    char buf[384];
+    if (cudaFuncGetAttributes(&fa, fn) == cudaSuccess)
+      std::snprintf(buf, sizeof buf, " [grid %lld, block %d, dynamic smem %zu; kernel: %d registers, %zu B static smem, max %d threads, max dynamic smem %d]",
+                    grid, block, dyn_smem, fa.numRegs, fa.sharedSizeBytes, fa.maxThreadsPerBlock, fa.maxDynamicSharedSizeBytes);
+    else { cudaGetLastError(); std::snprintf(buf, sizeof buf, " [grid %lld, block %d, dynamic smem %zu]", grid, block, dyn_smem); }
+    return fail(HB_ERR_CUDA, std::string("cudaLaunchKernelExC: ") + cudaGetErrorString(le) + buf);
+  }
   return HB_OK;
 }
 
@@ -459,9 +483,9 @@ LaunchShape pick_shape(const hb_system* s, const void* fn, long long n_traj, int
   // HBM-bound launches (light systems, the one-evaluation kernels): what counts is bytes in flight — full occupancy, small CTAs
   if (!heavy) return one_wave(128);
   // CTAs per SM for every candidate size, cached per kernel
-  struct Occ { int per_sm[17]; };
-  static std::mutex mu;
-  static std::map<std::tuple<int, const void*, int, int, int>, Occ> cache;
+  typedef ShapeOcc Occ;
+  std::mutex& mu = g_kcache_mu;
+  auto& cache = g_shape_cache;
   const auto key = std::make_tuple(dev, fn, in_d, out_d, kernel_layout == 2 ? 1 : 0);
   Occ occ;
   bool have = false;
@@ -812,6 +836,7 @@ hb_status hb_system_from_tape(int32_t m, int32_t n, const double* inertia, const
 
 void hb_system_free(hb_system* sys) {
   if (!sys) return;
+  for (const void* k : sys->jit_kernels) if (k) forget_kernel(k);   // the driver reuses kernel handles: drop what was cached under them
   for (auto& l : sys->libs) if (l) cudaLibraryUnload(l);
   delete sys;
 }

@@ -6,8 +6,11 @@ Timing: a CUDA graph of K one-step launches over a ring of 9 (in, out) buffer pa
 a graph of K launches ping-ponging between two buffers (a real stepping loop: L2-resident), and 16 steps fused per launch."""
 import os, subprocess, sys
 VARIANTS = [
-    ("default", {}),
-    ("round-1 final build", {"HB_LIB_PATH": "profiles/ab_libs/lib_r1_final.so"}),
+    ("AOT + flags, graph of 200 launches, best of 3 replays", {"HB_AB_BUILTIN": "1", "HB_AB_FLAGS": "1"}),
+    ("AOT + flags, graph of 200 launches, mean of 30 replays", {"HB_AB_BUILTIN": "1", "HB_AB_FLAGS": "1", "HB_AB_MEAN": "30"}),
+    ("AOT + flags, graph of 1000 launches, best of 3 replays", {"HB_AB_BUILTIN": "1", "HB_AB_FLAGS": "1", "HB_AB_K": "1000"}),
+    ("AOT + flags, graph of 1000 launches, mean of 6 replays", {"HB_AB_BUILTIN": "1", "HB_AB_FLAGS": "1", "HB_AB_K": "1000", "HB_AB_MEAN": "6"}),
+    ("AOT + flags, graph of 50 launches, mean of 120 replays", {"HB_AB_BUILTIN": "1", "HB_AB_FLAGS": "1", "HB_AB_K": "50", "HB_AB_MEAN": "120"}),
 ]
 def worker(name, log2n):
     sys.path.insert(0, ".")
@@ -16,12 +19,20 @@ def worker(name, log2n):
     from tests.common import BOXES
     N = 1 << log2n
     sid, lo, hi = BOXES[name]
-    s = hb.systems.from_def(hb.systems.DEFS[sid]())
+    s = hb.systems.builtin(sid) if os.environ.get("HB_AB_BUILTIN") else hb.systems.from_def(hb.systems.DEFS[sid]())
+    fl = torch.zeros(N, dtype=torch.int32, device="cuda") if os.environ.get("HB_AB_FLAGS") else None
     ring = 9
     ins = [s.batch_init_random(7 + r, 0, N, lo, hi) for r in range(ring)]
     outs = [torch.empty_like(b) for b in ins]
-    K = 200
+    K = int(os.environ.get('HB_AB_K', '200'))
     def timed(fn, reps=3):
+        if os.environ.get("HB_AB_MEAN"):          # mean over back-to-back repetitions (bench.py's way) instead of the best of 3
+            reps = int(os.environ["HB_AB_MEAN"])
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps): fn()
+            e1.record(); torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / reps
         best = 1e30
         for _ in range(reps):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -40,12 +51,14 @@ def worker(name, log2n):
         return g
     for i in range(3): s.batch_step(ins[i], 0.01, 1, out=outs[i])
     torch.cuda.synchronize()
-    g_ring = graph_of(lambda: [s.batch_step(ins[i % ring], 0.01, 1, out=outs[i % ring]) for i in range(K)])
+    g_ring = graph_of(lambda: [s.batch_step(ins[i % ring], 0.01, 1, out=outs[i % ring], flags=fl) for i in range(K)])
     a, b = ins[0].clone(), outs[0]
     g_chain = graph_of(lambda: [s.batch_step(a if i % 2 == 0 else b, 0.01, 1, out=b if i % 2 == 0 else a) for i in range(K)])
     t_ring = timed(g_ring.replay) / K
     t_chain = timed(g_chain.replay) / K
     t_16 = timed(lambda: [s.batch_step(ins[i % ring], 0.01, 16, out=outs[i % ring]) for i in range(8)]) / 8
+    from hamilton_b200 import _lib as LL
+    t_rkf = timed(lambda: [s.batch_step(ins[i % ring], 0.01, 1, integ=LL.RKF45_GSL, out=outs[i % ring]) for i in range(4)]) / 4
     # e2e: the same call on pinned HOST arrays (blocking), as bench.py's e2e leg
     import time
     src = ins[0].cpu()
@@ -57,8 +70,8 @@ def worker(name, log2n):
     for i in range(20): s.batch_step(h_in[i % 2], 0.01, 1, out=h_out[i % 2])
     torch.cuda.synchronize()
     t_e2e = (time.perf_counter() - t0) / 20
-    print("RESULT ring %.3f us/launch (%.3e steps/s)  chain %.3f us  fused16 %.3e  e2e %.3f ms/call (%.3e steps/s)" %
-          (t_ring * 1e3, N / t_ring * 1e3, t_chain * 1e3, N * 16 / t_16 * 1e3, t_e2e * 1e3, N / t_e2e))
+    print("RESULT ring %.3f us/launch (%.3e steps/s)  chain %.3f us  fused16 %.3e  stepHam(RKF45) %.3e /s  e2e %.3f ms/call (%.3e steps/s)" %
+          (t_ring * 1e3, N / t_ring * 1e3, t_chain * 1e3, N * 16 / t_16 * 1e3, N / t_rkf * 1e3, t_e2e * 1e3, N / t_e2e))
 if sys.argv[1] == "run":
     worker(sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 20)
 else:

@@ -31,5 +31,12 @@ def tape_args(system):
 
 
 def maxerr(a, b):
+    """Largest ABSOLUTE component-wise difference — the tolerance BASELINE.json's north_star states (|dq|, |dp| < 1e-10)."""
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return float(np.max(np.abs(a - b))) if a.size else 0.0
+
+
+def relerr(a, b):
+    """abs / (1 + |ref|): only for values too large for an absolute 1e-10 to be representable (|q| ~ 1e8: one ulp is 1e-8)."""
     a, b = np.asarray(a, float), np.asarray(b, float)
     return float(np.max(np.abs(a - b) / (1.0 + np.abs(b)))) if a.size else 0.0
