@@ -28,18 +28,18 @@ def _p(a):
     return a.ctypes.data_as(_dp)
 
 
-def harness(name, kind="aot", defines=()):
-    """Builds (once per session) the host image of the engine + the generated Sys of a built-in system."""
+def harness(name, kind="aot", defines=(), definition=None):
+    """Builds (once per session) the host image of the engine + the generated Sys of a built-in system (or of `definition`,
+    a hamilton_b200.systems *_def tuple traced like a user system)."""
     key = (name, kind, tuple(defines))
     if key in _cache:
         return _cache[key]
-    sid = BOXES[name][0]
-    if kind == "aot":
-        s = hb.systems.builtin(sid)
+    if kind == "aot" and definition is None:
+        s = hb.systems.builtin(BOXES[name][0])
     else:
         os.environ["HB_JIT_SKIP_COMPILE"] = "1"        # symbolic stage only: the host harness compiles the source itself
         try:
-            s = hb.systems.from_def(hb.systems.DEFS[sid]())
+            s = hb.systems.from_def(definition if definition is not None else hb.systems.DEFS[BOXES[name][0]]())
         finally:
             del os.environ["HB_JIT_SKIP_COMPILE"]
     holder = tempfile.TemporaryDirectory(prefix="hb_hostemu_")   # removed when the test session's cache is dropped
@@ -144,6 +144,29 @@ def test_engine_large_system_shared_memory_path_on_host(oracle_mod):
         dq, dp = o.ham_eqs(y[:12], y[12:])
         assert maxerr(dy, np.r_[dq, dp]) < 1e-11
     want, bad = o.batch_step(ys, 0, 0.01, 2)
+    for y, w in zip(ys, want):
+        got = y.copy()
+        assert lib.rk4_steps(_p(prm), _p(got), C.c_double(0.01), 2) == 0
+        assert maxerr(got, w) < 1e-10
+
+
+def test_engine_at_the_largest_supported_size_on_host(oracle_mod):
+    """n = HB_MAX_N = 16: a 16-link chain (System 32 16) traced as a user system — symbolic stage, generated hpre / hpost, the
+    16 x 16 LDL^T and the shared-memory RK4, against the oracle's tape interpreter (dense jets + explicit inverse)."""
+    from tests.common import tape_args
+    d = hb.systems.pendulum_chain_def([1.0] * 16, [1.0] * 16)
+    lib, prm, s = harness("chain16", kind="jit", definition=d)
+    assert (s.m, s.n) == (32, 16)
+    o = oracle_mod.OracleSystem.from_tape(*tape_args(s))
+    rng = np.random.default_rng(16)
+    ys = np.c_[rng.uniform(-np.pi, np.pi, size=(3, 16)), rng.uniform(-1, 1, size=(3, 16))]
+    for y in ys:
+        dy = np.empty(32)
+        assert lib.ham_eqs(_p(prm), _p(y), _p(dy)) == 0
+        dq, dp = o.ham_eqs(y[:16], y[16:])
+        assert maxerr(dy, np.r_[dq, dp]) < 1e-10
+    want, bad = o.batch_step(ys, 0, 0.01, 2)
+    assert bad == 0
     for y, w in zip(ys, want):
         got = y.copy()
         assert lib.rk4_steps(_p(prm), _p(got), C.c_double(0.01), 2) == 0

@@ -491,3 +491,19 @@ def test_evolve_ham_c_matches_oracle(oracle_mod):
     want3 = np.array([np.r_[r[:3], o3.velocities(r[:3], r[3:])] for r in ref3])
     got3 = hb.evolveHamC(s3, c3, ts3)
     assert maxerr(np.array([np.r_[c.cfgPositions, c.cfgVelocities] for c in got3]), want3) < 1e-9
+
+
+def test_largest_supported_system_n16(oracle_mod):
+    """n = HB_MAX_N = 16 (n = 13..16 untested): a 16-link chain (System 32 16) as a tape system — NVRTC build of
+    hamEqs, RK4 and the adaptive stepper against the oracle's tape interpreter.  (A 16 x 16 packed mass matrix is 136 doubles:
+    it cannot live in registers, the kernel spills to local memory — correct, slow)"""
+    s = hb.systems.from_def(hb.systems.pendulum_chain_def([1.0] * 16, [1.0] * 16))
+    o = oracle_mod.OracleSystem.from_tape(*tape_args(s))
+    rng = np.random.default_rng(1616)
+    y = np.c_[rng.uniform(-np.pi, np.pi, size=(96, 16)), rng.uniform(-1, 1, size=(96, 16))]
+    fl = np.zeros(96, np.int32)
+    assert maxerr(s.batch_ham_eqs(y, flags=fl), o.batch_ham_eqs(y)) < TOL and not fl.any()
+    yo, bad = o.batch_step(y, 0, 0.01, 2, threads=oracle_mod.max_threads())
+    assert bad == 0 and maxerr(s.batch_step(y, 0.01, 2, integ=L.RK4), yo) < 2 * TOL
+    yo, bad = o.batch_step(y[:16], 1, 0.01, 1, threads=oracle_mod.max_threads())
+    assert bad == 0 and maxerr(s.batch_step(y[:16], 0.01, 1, integ=L.RKF45_GSL), yo) < TOL
