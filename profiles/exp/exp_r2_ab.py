@@ -6,11 +6,9 @@ Timing: a CUDA graph of K one-step launches over a ring of 9 (in, out) buffer pa
 a graph of K launches ping-ponging between two buffers (a real stepping loop: L2-resident), and 16 steps fused per launch."""
 import os, subprocess, sys
 VARIANTS = [
-    ("AOT + flags, graph of 200 launches, best of 3 replays", {"HB_AB_BUILTIN": "1", "HB_AB_FLAGS": "1"}),
-    ("AOT + flags, graph of 200 launches, mean of 30 replays", {"HB_AB_BUILTIN": "1", "HB_AB_FLAGS": "1", "HB_AB_MEAN": "30"}),
-    ("AOT + flags, graph of 1000 launches, best of 3 replays", {"HB_AB_BUILTIN": "1", "HB_AB_FLAGS": "1", "HB_AB_K": "1000"}),
-    ("AOT + flags, graph of 1000 launches, mean of 6 replays", {"HB_AB_BUILTIN": "1", "HB_AB_FLAGS": "1", "HB_AB_K": "1000", "HB_AB_MEAN": "6"}),
-    ("AOT + flags, graph of 50 launches, mean of 120 replays", {"HB_AB_BUILTIN": "1", "HB_AB_FLAGS": "1", "HB_AB_K": "50", "HB_AB_MEAN": "120"}),
+    ("ahead-of-time kernel (default build)", {"HB_AB_BUILTIN": "1"}),
+    ("ahead-of-time kernel, right-looking LDL^T (HB_LDLT_RIGHT=1)", {"HB_AB_BUILTIN": "1", "HB_LIB_PATH": "profiles/ab_libs/lib_chain12_ldlt_right.so"}),
+    ("round-1 final build", {"HB_AB_BUILTIN": "1", "HB_LIB_PATH": "profiles/ab_libs/lib_r1_final.so"}),
 ]
 def worker(name, log2n):
     sys.path.insert(0, ".")
