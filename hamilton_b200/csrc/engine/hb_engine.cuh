@@ -441,9 +441,8 @@ HB_DEV void hb_mass(const double* wJ, const double* Jv, double* A) {
   });
 }
 
-#ifndef HB_LDLT_RIGHT
-#define HB_LDLT_RIGHT 0
-#endif
+// (A right-looking ordering of the LDL^T updates — runs of DFMAs sharing their first operand, for the operand-reuse cache —
+// measured no different on the 12 x 12 chain: profiles/r2l/ab_chain12_ldlt.txt.)
 // Solve A x = b for the packed SPD mass matrix; A is destroyed.  Replaces the reference's explicit
 // `inv jmj` (src/Numeric/Hamilton.hs:381); a non-positive pivot is the analogue of hmatrix's
 // singular-matrix exception.  N = 1, 2: closed form with ONE reciprocal (shortest dependency chain);
@@ -504,44 +503,6 @@ HB_DEV void hb_spd_solve_v(double* A, const BV b, double* x, int& minpiv) {
     x[1] = fma(c01, b0, fma(c11, b1, c12 * b2)) * id;
     x[2] = fma(c02, b0, fma(c12, b1, c22 * b2)) * id;
 #endif
-#if HB_LDLT_RIGHT
-  } else {
-    // right-looking LDL^T (experiment switch): step k scales column k and applies the rank-1 update to the trailing
-    // triangle at once, A_ij -= l_ik a_jk — runs of independent DFMAs whose first operand (l_ik) repeats, which the
-    // operand-reuse cache turns from 3-clock three-register issues into 2-clock ones.  Same pivots, same flags.
-    double invd[N];
-    hb_static_for<0, N>([&](auto kt) {
-      HB_IDX(k, kt);
-      const double d = A[hb_tri(k, k)];
-      hb_piv(minpiv, d);
-      const double id = hb_rcp(d);
-      invd[k] = id;
-      double col[N - k > 1 ? N - k - 1 : 1];                    // a_jk (unscaled), j = k+1 .. N-1
-      hb_static_for<k + 1, N>([&](auto jt) { HB_IDX(j, jt); col[j - k - 1] = A[hb_tri(j, k)]; });
-      hb_static_for<k + 1, N>([&](auto it) {
-        HB_IDX(i, it);
-        const double lik = col[i - k - 1] * id;
-        A[hb_tri(i, k)] = lik;
-        hb_static_for<k + 1, i + 1>([&](auto jt) { HB_IDX(j, jt); A[hb_tri(i, j)] = fma(-lik, col[j - k - 1], A[hb_tri(i, j)]); });
-      });
-    });
-    hb_static_for<0, N>([&](auto jt) {   // L y = b
-      HB_IDX(j, jt);
-      double t = b(j);
-      hb_static_for<0, j>([&](auto kt) { HB_IDX(k, kt); t = fma(-A[hb_tri(j, k)], x[k], t); });
-      x[j] = t;
-    });
-#pragma unroll
-    for (int j = 0; j < N; j++) x[j] *= invd[j];   // D z = y
-    hb_static_for<0, N>([&](auto rt) {   // L^T x = z
-      HB_IDX(r, rt);
-      constexpr int j = N - 1 - r;
-      double t = x[j];
-      hb_static_for<j + 1, N>([&](auto kt) { HB_IDX(k, kt); t = fma(-A[hb_tri(k, j)], x[k], t); });
-      x[j] = t;
-    });
-  }
-#else
   } else {
     // LDL^T, fully unrolled by compile-time recursion (a rolled loop would index A dynamically and push it to local memory)
     double invd[N];
@@ -581,7 +542,6 @@ HB_DEV void hb_spd_solve_v(double* A, const BV b, double* x, int& minpiv) {
       x[j] = t;
     });
   }
-#endif
 }
 
 // wJ[e] = w[row(e)] * J[e]
@@ -946,9 +906,6 @@ HB_DEV void hb_rkf45_to(HbCtx& cx, const double* prm, const double* w, double (&
 #ifndef HB_LAYSPEC
 #define HB_LAYSPEC 1
 #endif
-#ifndef HB_L2_AHEAD
-#define HB_L2_AHEAD 0      // 1: besides the cp.async of the next Phase, pull the one after it into L2
-#endif
 #ifndef HB_ASYNC_STAGE
 #define HB_ASYNC_STAGE 1   // small systems, array of records: the next Phase is staged by cp.async into shared memory (0: plain loads)
 #endif
@@ -1195,7 +1152,6 @@ HB_DEV void hb_traj_upos(const HbKArgs& a, I i, const double* yin, const double*
         const unsigned inext = i + istride;                                                                \
         more = inext < N;                                                                                  \
         if (more) hb_async_load<DIN>(nxt, nxt_s, cstride, a.in + (size_t)inext * DIN);                     \
-        if (HB_L2_AHEAD && !a.host_io) { if (inext + istride < N) hb_prefetch_l2<DIN, unsigned>(a.in, inext + istride, N, lay); } \
         HB_PROCESS_(NAME, i, yin)                                                                          \
         i = inext;                                                                                         \
         { double* tp = cur; cur = nxt; nxt = tp; const unsigned ts = cur_s; cur_s = nxt_s; nxt_s = ts; }   \
