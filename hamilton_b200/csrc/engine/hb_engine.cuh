@@ -49,8 +49,9 @@
 #define HB_BIG_N 8
 #define HB_DYN_DOUBLES(NCOORD, NE_) ((NCOORD) >= HB_BIG_N ? 3 * 2 * (NCOORD) + (NE_) : 0)
 // Dynamic shared memory of every kernel (hb_dsm), in this order — csrc/runtime.cpp dyn_smem_bytes() computes the same sizes:
-//   small systems (n < HB_BIG_N):  [ sin/cos table image: HB_TAB_BYTES ]  [ stage: 2 x DIN doubles per thread, the cp.async
-//                                  landing zone of the thread's next Phase ]  [ xp ]
+//   small systems (n < HB_BIG_N):  [ sin/cos table image: HB_TAB_BYTES, systems with sin/cos only ]  [ stage: 2 x DIN doubles per
+//                                  thread, the cp.async landing zone of the thread's next Phase: stepping kernels of HEAVY
+//                                  systems only ]  [ xp ]
 //   large systems:                 [ RK vectors + parked values: HB_DYN_DOUBLES per thread ]  [ xp ]
 //   xp = DOUT doubles per thread, the warps' transpose buffers for host-memory stores; present only when a.layout == 2
 //   and DOUT is even and <= HB_WSTORE_MAXD.
@@ -88,7 +89,7 @@ struct HbKArgs {
   unsigned long long seed;
   long long first;
   int host_io;            // 1: `in` / `out` are page-locked HOST memory accessed over PCIe (no L2 prefetches of them)
-  int pad_;
+  int contiguous;         // 1: CTA b starts at tiles b W .. b W + W - 1 (multi-wave grids of long kernels), 0: tiles spread over CTAs
   double prm[HB_MAXP];    // runtime parameters (HB_OP_PARAM leaves); for init_random: lo[0..D), hi[0..D)
 };
 
@@ -906,6 +907,9 @@ HB_DEV void hb_rkf45_to(HbCtx& cx, const double* prm, const double* w, double (&
 #ifndef HB_LAYSPEC
 #define HB_LAYSPEC 1
 #endif
+#ifndef HB_REG_PREFETCH
+#define HB_REG_PREFETCH 1  // plain-load path, records of <= 8 doubles: register prefetch of the next Phase
+#endif
 #ifndef HB_ASYNC_STAGE
 #define HB_ASYNC_STAGE 1   // small systems, array of records: the next Phase is staged by cp.async into shared memory (0: plain loads)
 #endif
@@ -1121,12 +1125,13 @@ HB_DEV void hb_traj_upos(const HbKArgs& a, I i, const double* yin, const double*
     constexpr bool ASYNC = SMALL && HB_ASYNC_STAGE && DIN % 2 == 0 && STEPPING && S::HEAVY;                \
     const unsigned N = (unsigned)a.N;                                                                      \
     const unsigned istride = gridDim.x * blockDim.x;   /* trajectories per round */                        \
-    unsigned i = (blockIdx.x + gridDim.x * (threadIdx.x >> 5)) * 32u + (threadIdx.x & 31u);                \
+    unsigned i = a.contiguous ? blockIdx.x * blockDim.x + threadIdx.x                                      \
+                              : (blockIdx.x + gridDim.x * (threadIdx.x >> 5)) * 32u + (threadIdx.x & 31u); \
     const int lay = hb_lay_of<LAY>(a);                                                                     \
     /* carve the dynamic shared memory (layout: HB_DYN_DOUBLES) */                                         \
     HbTab* tab = SMALL ? reinterpret_cast<HbTab*>(hb_dsm) : big_tab;                                       \
-    double* stage = hb_dsm + HB_TAB_BYTES / 8;                                                             \
-    double* xp = SMALL ? stage + 2 * DIN * blockDim.x : hb_dsm + HB_DYN_DOUBLES(S::N, S::NE) * blockDim.x; \
+    double* stage = hb_dsm + (S::TRIG ? HB_TAB_BYTES / 8 : 0);                                             \
+    double* xp = SMALL ? stage + (ASYNC ? 2 * DIN * blockDim.x : 0) : hb_dsm + HB_DYN_DOUBLES(S::N, S::NE) * blockDim.x; \
     xp = (lay == 2 && DOUT % 2 == 0 && DOUT <= HB_WSTORE_MAXD) ? xp + (threadIdx.x & ~31u) * DOUT : nullptr; \
     HB_PDL_LAUNCH_DEPENDENTS();                                                                            \
     if constexpr (S::TRIG) hb_tab_issue(tab);                                                              \
@@ -1155,6 +1160,19 @@ HB_DEV void hb_traj_upos(const HbKArgs& a, I i, const double* yin, const double*
         HB_PROCESS_(NAME, i, yin)                                                                          \
         i = inext;                                                                                         \
         { double* tp = cur; cur = nxt; nxt = tp; const unsigned ts = cur_s; cur_s = nxt_s; nxt_s = ts; }   \
+      }                                                                                                    \
+    } else if constexpr (DIN <= 8 && HB_REG_PREFETCH) {   /* plain loads, small records: the next Phase is loaded into registers under this one's arithmetic (light kernels: the exposed L2 latency of a load at the top of every trajectory costs 8-30 %, profiles/r2n) */ \
+      double yin[DIN];                                                                                     \
+      if (more) hb_load<DIN, unsigned>(a.in, i, N, lay, yin);                                              \
+      while (more) {                                                                                       \
+        double ycur[DIN];                                                                                  \
+        hb_copy<DIN>(yin, ycur);                                                                           \
+        const unsigned inext = i + istride;                                                                \
+        more = inext < N;                                                                                  \
+        if (more) hb_load<DIN, unsigned>(a.in, inext, N, lay, yin);                                        \
+        if (HB_PRE_L2 && !a.host_io) { if (inext + istride < N) hb_prefetch_l2<DIN, unsigned>(a.in, inext + istride, N, lay); } \
+        HB_PROCESS_(NAME, i, ycur)                                                                         \
+        i = inext;                                                                                         \
       }                                                                                                    \
     } else {                                                                                               \
       double yin[DIN];                                                                                     \

@@ -30,7 +30,7 @@ struct HbKArgs {
   const double* in; double* out; int* flags; const double* ts;
   long long N; double dt; double dt6; double dth; int nsteps; int layout; int s; int substeps;
   unsigned long long seed; long long first;
-  int host_io; int pad_;
+  int host_io; int contiguous;
   double prm[HB_MAXP];
 };
 enum { K_STEP_RK4 = 0, K_STEP_RKF45, K_EVOLVE_RK4, K_EVOLVE_RKF45, K_HAM_EQS, K_TO_PHASE, K_FROM_PHASE, K_ENERGIES, K_UPOS, K_COUNT };
@@ -239,6 +239,7 @@ struct hb_system {
   int dyn_doubles = 0;                 // dynamic shared memory per thread (doubles) every kernel of this system is launched with
   int rhs_cost = 0;                    // system compiler's cost model of one hamEqs evaluation
   bool heavy = false;                  // Sys::HEAVY: one RK4 step is issue-bound, not HBM-bound (launch-shape heuristic)
+  bool trig = false;                   // Sys::TRIG: the kernels stage the sin/cos table image in dynamic shared memory
   std::string source;                  // generated Sys struct
   // JIT: small systems compile all kernels in one NVRTC program at creation (cubins[K_COUNT] shared slot 0);
   // large ones compile each kernel on first use (a 12-coordinate chain takes ~10 s per kernel).
@@ -446,8 +447,14 @@ hb_status launch(const void* fn, const HbKArgs& a, long long grid, cudaStream_t 
 }
 
 // Dynamic shared memory of one launch; mirrors the layout documented at HB_DYN_DOUBLES in engine/hb_engine.cuh.
-size_t dyn_smem_bytes(const hb_system* s, int block, int in_d, int out_d, int kernel_layout) {
-  size_t b = s->n >= HB_BIG_N ? (size_t)s->dyn_doubles * sizeof(double) * block : (size_t)HB_TAB_BYTES + (size_t)2 * in_d * sizeof(double) * block;
+bool stepping_kernel(int kid) { return kid == K_STEP_RK4 || kid == K_STEP_RKF45 || kid == K_EVOLVE_RK4 || kid == K_EVOLVE_RKF45; }
+size_t dyn_smem_bytes(const hb_system* s, int kid, int block, int in_d, int out_d, int kernel_layout) {
+  size_t b;
+  if (s->n >= HB_BIG_N) b = (size_t)s->dyn_doubles * sizeof(double) * block;
+  else {
+    b = s->trig ? (size_t)HB_TAB_BYTES : 0;
+    if (s->heavy && stepping_kernel(kid) && in_d % 2 == 0) b += (size_t)2 * in_d * sizeof(double) * block;   // cp.async stage (engine: ASYNC)
+  }
   if (kernel_layout == 2 && out_d % 2 == 0 && out_d <= HB_WSTORE_MAXD) b += (size_t)out_d * sizeof(double) * block;
   return b;
 }
@@ -465,20 +472,22 @@ size_t dyn_smem_bytes(const hb_system* s, int block, int in_d, int out_d, int ke
 // cached) with   waste = [frac > 0] max(0, RHO - frac x warps/SM)  +  TABLE x CTAs/SM   (in units of one tile's issue time;
 // RHO = 8: one warp alone needs ~8x its issue-bound share, TABLE = 2) and takes the cheapest, ties to more warps.
 // HB_BLOCK / HB_GRID_WAVES override (experiments).
-struct LaunchShape { int block; long long grid; };
-LaunchShape pick_shape(const hb_system* s, const void* fn, long long n_traj, int in_d, int out_d, int kernel_layout, bool heavy) {
+struct LaunchShape { int block; long long grid; int contiguous = 0; };
+LaunchShape pick_shape(const hb_system* s, int kid, const void* fn, long long n_traj, int in_d, int out_d, int kernel_layout, bool heavy) {
   static const int block_env = [] { const char* e = std::getenv("HB_BLOCK"); int t = e ? std::atoi(e) : 0; return (t >= 32 && t <= 1024 && t % 32 == 0) ? t : 0; }();
   static const double waves_env = [] { const char* e = std::getenv("HB_GRID_WAVES"); double t = e ? std::atof(e) : 0.0; return (t > 0 && t <= 4096) ? t : 0.0; }();
   int dev = 0, sms = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) { cudaGetLastError(); sms = 148; }
   auto one_wave = [&](int block) -> LaunchShape {
-    const int slots = resident_ctas(fn, block, dyn_smem_bytes(s, block, in_d, out_d, kernel_layout));
+    const int slots = resident_ctas(fn, block, dyn_smem_bytes(s, kid, block, in_d, out_d, kernel_layout));
     long long blocks = (n_traj + block - 1) / block;
     const long long cap = (long long)((double)(slots > 0 ? slots : sms) * (waves_env > 0 ? waves_env : 1.0));
     if (blocks > cap) blocks = cap;
     return LaunchShape{block, blocks < 1 ? 1 : blocks};
   };
-  if (s->n >= HB_BIG_N) return one_wave(HB_BLOCK_OF(s->n));
+  // Large systems: long kernels (150 us for the 12-link chain) on 2 CTAs per SM — TWO waves with the contiguous tile map (the
+  // CTAs of the second wave go to whichever SM frees up first: dynamic balance, 6 % against one static wave, profiles/r2n)
+  if (s->n >= HB_BIG_N) { LaunchShape sh = one_wave(HB_BLOCK_OF(s->n)); const long long need = (n_traj + sh.block - 1) / sh.block; sh.grid = std::min<long long>(need, 2 * sh.grid); sh.contiguous = 1; return sh; }
   if (block_env) return one_wave(block_env);
   // HBM-bound launches (light systems, the one-evaluation kernels): what counts is bytes in flight — full occupancy, small CTAs
   if (!heavy) return one_wave(128);
@@ -501,7 +510,7 @@ LaunchShape pick_shape(const hb_system* s, const void* fn, long long n_traj, int
     for (int w = 0; w <= 16; w++) {
       occ.per_sm[w] = 0;
       if (w < 4 || 32 * w > max_threads) continue;
-      const int slots = resident_ctas(fn, 32 * w, dyn_smem_bytes(s, 32 * w, in_d, out_d, kernel_layout));
+      const int slots = resident_ctas(fn, 32 * w, dyn_smem_bytes(s, kid, 32 * w, in_d, out_d, kernel_layout));
       occ.per_sm[w] = slots > 0 ? slots / sms : 0;
     }
     std::lock_guard<std::mutex> lk(mu);
@@ -536,8 +545,10 @@ bool heavy_launch(const hb_system* s, int kid, const HbKArgs& a) {
   return kid == K_STEP_RKF45 || kid == K_EVOLVE_RK4 || kid == K_EVOLVE_RKF45;
 }
 hb_status launch_sys(const hb_system* s, int kid, const void* fn, const HbKArgs& a, long long n_traj, cudaStream_t st, int in_d, int out_d) {
-  const LaunchShape sh = pick_shape(s, fn, n_traj, in_d, out_d, a.layout, heavy_launch(s, kid, a));
-  return launch(fn, a, sh.grid, st, sh.block, dyn_smem_bytes(s, sh.block, in_d, out_d, a.layout));
+  const LaunchShape sh = pick_shape(s, kid, fn, n_traj, in_d, out_d, a.layout, heavy_launch(s, kid, a));
+  HbKArgs ac = a;
+  ac.contiguous = sh.contiguous;
+  return launch(fn, ac, sh.grid, st, sh.block, dyn_smem_bytes(s, kid, sh.block, in_d, out_d, a.layout));
 }
 
 void fill_params(const hb_system* s, HbKArgs& a) {
@@ -654,8 +665,8 @@ hb_status run_batch(const hb_system* sys, int kid, HbKArgs a, int64_t N, hb_mems
   }
   cudaStream_t s_up = g_scratch.streams[0], s_k = g_scratch.streams[1], s_down = g_scratch.streams[2];
   if ((rc = g_scratch.need_events((int)(2 * chunks) + 1))) return rc;
-  (void)pick_shape(sys, fn, N, in_d, out_d, hybrid ? 2 : a.layout, heavy_launch(sys, kid, a));   // (keeps the occupancy queries out of a capture)
-  (void)pick_shape(sys, fn, (N + chunks - 1) / chunks, in_d, out_d, hybrid ? 2 : a.layout, heavy_launch(sys, kid, a));
+  (void)pick_shape(sys, kid, fn, N, in_d, out_d, hybrid ? 2 : a.layout, heavy_launch(sys, kid, a));   // (keeps the occupancy queries out of a capture)
+  (void)pick_shape(sys, kid, fn, (N + chunks - 1) / chunks, in_d, out_d, hybrid ? 2 : a.layout, heavy_launch(sys, kid, a));
   auto enqueue = [&]() -> hb_status {
     if (ts) {
       double* dts = (double*)((char*)din + in_bytes);
@@ -789,7 +800,7 @@ hb_status hb_system_builtin(hb_builtin id, const double* params, int32_t n_param
   if (hb_aot_kargs_size() != sizeof(HbKArgs)) { delete s; return fail(HB_ERR_INVALID, "internal: host/device HbKArgs layout mismatch"); }
   hb::GeneratedSystem g;
   std::string err;
-  if (hb::generate_system(spec, std::string("HbSys_") + hb::builtin_name(id) + (s->baked ? "_dflt" : ""), g, err)) { s->source = g.source; s->rhs_cost = g.rhs_cost; s->heavy = g.heavy; }
+  if (hb::generate_system(spec, std::string("HbSys_") + hb::builtin_name(id) + (s->baked ? "_dflt" : ""), g, err)) { s->source = g.source; s->rhs_cost = g.rhs_cost; s->heavy = g.heavy; s->trig = g.trig; }
   *out = s;
   return HB_OK;
 }
@@ -820,6 +831,7 @@ hb_status hb_system_from_tape(int32_t m, int32_t n, const double* inertia, const
   s->source = g.source;
   s->rhs_cost = g.rhs_cost;
   s->heavy = g.heavy;
+  s->trig = g.trig;
   s->gen = g;
   s->dyn_doubles = HB_DYN_DOUBLES(n, g.ne);
   s->arch = jit_arch();

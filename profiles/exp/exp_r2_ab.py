@@ -6,9 +6,8 @@ Timing: a CUDA graph of K one-step launches over a ring of 9 (in, out) buffer pa
 a graph of K launches ping-ponging between two buffers (a real stepping loop: L2-resident), and 16 steps fused per launch."""
 import os, subprocess, sys
 VARIANTS = [
-    ("ahead-of-time kernel (default build)", {"HB_AB_BUILTIN": "1"}),
-    ("ahead-of-time kernel, right-looking LDL^T (HB_LDLT_RIGHT=1)", {"HB_AB_BUILTIN": "1", "HB_LIB_PATH": "profiles/ab_libs/lib_chain12_ldlt_right.so"}),
-    ("round-1 final build", {"HB_AB_BUILTIN": "1", "HB_LIB_PATH": "profiles/ab_libs/lib_r1_final.so"}),
+    ("default", {}),
+    ("round-1 final build", {"HB_LIB_PATH": "profiles/ab_libs/lib_r1_final.so"}),
 ]
 def worker(name, log2n):
     sys.path.insert(0, ".")
