@@ -456,7 +456,12 @@ size_t dyn_smem_bytes(const hb_system* s, int kid, int block, int in_d, int out_
     if (s->heavy && stepping_kernel(kid) && in_d % 2 == 0) b += (size_t)2 * in_d * sizeof(double) * block;   // cp.async stage (engine: ASYNC)
   }
   if (kernel_layout == 2 && out_d % 2 == 0 && out_d <= HB_WSTORE_MAXD) b += (size_t)out_d * sizeof(double) * block;
-  return b;
+  // Empirical: a kernel that asks for NO shared memory at all gets the whole 256 KB as L1, and the HBM-bound two-body step runs
+  // 13 % slower that way than with a 64 KB carve-out (25.4 vs 22.1 us, profiles/r2q/ab_two_body.txt; pendulum and 1-D spring
+  // within 2 %).  Every launch therefore asks for at least 8 KB per CTA; the kernels never touch the padding.
+  if (b < 8192) b = 8192;
+  static const size_t extra = [] { const char* e = std::getenv("HB_EXTRA_SMEM"); long t = e ? std::atol(e) : 0; return (t > 0 && t <= 200000) ? (size_t)t : (size_t)0; }();
+  return b + extra;   // HB_EXTRA_SMEM: experiment knob (occupancy / L1 carve-out studies)
 }
 // Launch shape of one kernel of a system: CTA size and grid.
 // Large systems: HB_BLOCK_OF threads (their shared-memory layout is compiled for it), one resident wave.

@@ -7,7 +7,13 @@ a graph of K launches ping-ponging between two buffers (a real stepping loop: L2
 import os, subprocess, sys
 VARIANTS = [
     ("default", {}),
-    ("round-1 final build", {"HB_LIB_PATH": "profiles/ab_libs/lib_r1_final.so"}),
+    ("+ 8 KB unused dynamic smem per CTA", {"HB_EXTRA_SMEM": "8192"}),
+    ("+ 16 KB", {"HB_EXTRA_SMEM": "16384"}),
+    ("+ 24 KB", {"HB_EXTRA_SMEM": "24576"}),
+    ("+ 33 KB (6 CTAs/SM, the r2n shape)", {"HB_EXTRA_SMEM": "33792"}),
+    ("+ 44 KB (5 CTAs/SM)", {"HB_EXTRA_SMEM": "45056"}),
+    ("+ 56 KB (4 CTAs/SM)", {"HB_EXTRA_SMEM": "57344"}),
+    ("CTA 256 + 33 KB", {"HB_BLOCK": "256", "HB_EXTRA_SMEM": "33792"}),
 ]
 def worker(name, log2n):
     sys.path.insert(0, ".")
