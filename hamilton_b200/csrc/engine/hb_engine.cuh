@@ -1260,7 +1260,10 @@ HB_DEV void hb_body_init_random(const HbKArgs& a) {
 // The adaptive kernels keep six stage vectors live and reach 200+ registers (2 CTAs/SM: two warps per scheduler cannot
 // cover the 8-clock FP64 latency).  Capping small systems at 128 registers (4 CTAs/SM) spills a few stage vectors to
 // local memory and still wins: double pendulum +10 %, triple pendulum +11 % (profiles/r1z/ab_rkf45_regs.txt).
-#define HB_LB_RKF45(SYS) __launch_bounds__((SYS::N <= 3 ? 256 : HB_MAXBLOCK_OF(SYS::N)), (SYS::N <= 3 ? 2 : 0))
+#ifndef HB_RKF45_CTAS
+#define HB_RKF45_CTAS(NCOORD) 2     // CTAs of 256 threads per SM the adaptive kernels of small systems are compiled for (2: 128 registers)
+#endif
+#define HB_LB_RKF45(SYS) __launch_bounds__((SYS::N <= 3 ? 256 : HB_MAXBLOCK_OF(SYS::N)), (SYS::N <= 3 ? HB_RKF45_CTAS(SYS::N) : 0))
 #endif
 #define HB_DEFINE_KERNEL_Y(SYS, PFX, KIND) extern "C" __global__ void HB_LB_RKF45(SYS) PFX##_##KIND(const __grid_constant__ HbKArgs a) { HB_TAB_DECL(SYS); hb_body_##KIND<SYS, -1>(a, hb_tab); }
 #define HB_DEFINE_KERNEL_step_rkf45(SYS, PFX) HB_DEFINE_KERNEL_L(SYS, PFX, step_rkf45, HB_LB_RKF45(SYS), 0)

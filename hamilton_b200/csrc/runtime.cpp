@@ -240,6 +240,7 @@ struct hb_system {
   int rhs_cost = 0;                    // system compiler's cost model of one hamEqs evaluation
   bool heavy = false;                  // Sys::HEAVY: one RK4 step is issue-bound, not HBM-bound (launch-shape heuristic)
   bool trig = false;                   // Sys::TRIG: the kernels stage the sin/cos table image in dynamic shared memory
+  double intensity = 0;                // issue clocks / HBM clocks of one RK4 step (system compiler's estimate)
   std::string source;                  // generated Sys struct
   // JIT: small systems compile all kernels in one NVRTC program at creation (cubins[K_COUNT] shared slot 0);
   // large ones compile each kernel on first use (a 12-coordinate chain takes ~10 s per kernel).
@@ -494,8 +495,19 @@ LaunchShape pick_shape(const hb_system* s, int kid, const void* fn, long long n_
   // CTAs of the second wave go to whichever SM frees up first: dynamic balance, 6 % against one static wave, profiles/r2n)
   if (s->n >= HB_BIG_N) { LaunchShape sh = one_wave(HB_BLOCK_OF(s->n)); const long long need = (n_traj + sh.block - 1) / sh.block; sh.grid = std::min<long long>(need, 2 * sh.grid); sh.contiguous = 1; return sh; }
   if (block_env) return one_wave(block_env);
-  // HBM-bound launches (light systems, the one-evaluation kernels): what counts is bytes in flight — full occupancy, small CTAs
-  if (!heavy) return one_wave(128);
+  // HBM-bound launches (light systems, the one-evaluation kernels): what counts is bytes in flight — full occupancy, small CTAs.
+  // The most HBM-bound of them (two-body, 1-D spring: issue/HBM estimate below 1.2; the one-evaluation kernels) stream best as
+  // FOUR waves with the contiguous tile map (two-body 23.1 us against 25.1 for one spread wave, 1-D spring 10.9 against 11.4);
+  // the pendulum (1.4) is fastest as one spread wave (14.8 against 17.0) — profiles/r2s.
+  if (!heavy) {
+    LaunchShape sh = one_wave(128);
+    if (waves_env <= 0 && (!stepping_kernel(kid) || s->intensity < 1.2)) {
+      const long long need = (n_traj + sh.block - 1) / sh.block;
+      sh.grid = std::min<long long>(need, 4 * sh.grid);
+      sh.contiguous = 1;
+    }
+    return sh;
+  }
   // CTAs per SM for every candidate size, cached per kernel
   typedef ShapeOcc Occ;
   std::mutex& mu = g_kcache_mu;
@@ -552,7 +564,8 @@ bool heavy_launch(const hb_system* s, int kid, const HbKArgs& a) {
 hb_status launch_sys(const hb_system* s, int kid, const void* fn, const HbKArgs& a, long long n_traj, cudaStream_t st, int in_d, int out_d) {
   const LaunchShape sh = pick_shape(s, kid, fn, n_traj, in_d, out_d, a.layout, heavy_launch(s, kid, a));
   HbKArgs ac = a;
-  ac.contiguous = sh.contiguous;
+  static const int contig_env = [] { const char* e = std::getenv("HB_CONTIGUOUS"); return e ? std::atoi(e) : -1; }();   // experiment knob
+  ac.contiguous = contig_env >= 0 ? contig_env : sh.contiguous;
   return launch(fn, ac, sh.grid, st, sh.block, dyn_smem_bytes(s, kid, sh.block, in_d, out_d, a.layout));
 }
 
@@ -805,7 +818,7 @@ hb_status hb_system_builtin(hb_builtin id, const double* params, int32_t n_param
   if (hb_aot_kargs_size() != sizeof(HbKArgs)) { delete s; return fail(HB_ERR_INVALID, "internal: host/device HbKArgs layout mismatch"); }
   hb::GeneratedSystem g;
   std::string err;
-  if (hb::generate_system(spec, std::string("HbSys_") + hb::builtin_name(id) + (s->baked ? "_dflt" : ""), g, err)) { s->source = g.source; s->rhs_cost = g.rhs_cost; s->heavy = g.heavy; s->trig = g.trig; }
+  if (hb::generate_system(spec, std::string("HbSys_") + hb::builtin_name(id) + (s->baked ? "_dflt" : ""), g, err)) { s->source = g.source; s->rhs_cost = g.rhs_cost; s->heavy = g.heavy; s->trig = g.trig; s->intensity = g.intensity; }
   *out = s;
   return HB_OK;
 }
@@ -837,6 +850,7 @@ hb_status hb_system_from_tape(int32_t m, int32_t n, const double* inertia, const
   s->rhs_cost = g.rhs_cost;
   s->heavy = g.heavy;
   s->trig = g.trig;
+  s->intensity = g.intensity;
   s->gen = g;
   s->dyn_doubles = HB_DYN_DOUBLES(n, g.ne);
   s->arch = jit_arch();

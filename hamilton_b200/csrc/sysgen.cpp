@@ -535,6 +535,7 @@ bool generate_system(const SystemSpec& spec, const std::string& name, GeneratedS
   out.ne = SH.ok ? (int)SH.carried.size() : 0;
   out.rhs_cost = SH.ok ? SH.cost_sym : SH.cost_direct;
   out.heavy = heavy;
+  out.intensity = issue_clk / hbm_clk;
   out.trig = trig;
   return true;
 }

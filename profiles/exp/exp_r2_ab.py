@@ -6,14 +6,12 @@ Timing: a CUDA graph of K one-step launches over a ring of 9 (in, out) buffer pa
 a graph of K launches ping-ponging between two buffers (a real stepping loop: L2-resident), and 16 steps fused per launch."""
 import os, subprocess, sys
 VARIANTS = [
-    ("default", {}),
-    ("+ 8 KB unused dynamic smem per CTA", {"HB_EXTRA_SMEM": "8192"}),
-    ("+ 16 KB", {"HB_EXTRA_SMEM": "16384"}),
-    ("+ 24 KB", {"HB_EXTRA_SMEM": "24576"}),
-    ("+ 33 KB (6 CTAs/SM, the r2n shape)", {"HB_EXTRA_SMEM": "33792"}),
-    ("+ 44 KB (5 CTAs/SM)", {"HB_EXTRA_SMEM": "45056"}),
-    ("+ 56 KB (4 CTAs/SM)", {"HB_EXTRA_SMEM": "57344"}),
-    ("CTA 256 + 33 KB", {"HB_BLOCK": "256", "HB_EXTRA_SMEM": "33792"}),
+    ("default (tiles spread over CTAs, one wave)", {}),
+    ("contiguous tile map, one wave", {"HB_CONTIGUOUS": "1"}),
+    ("contiguous tile map, 2 waves (the round-1 shape)", {"HB_CONTIGUOUS": "1", "HB_GRID_WAVES": "2"}),
+    ("contiguous tile map, 4 waves", {"HB_CONTIGUOUS": "1", "HB_GRID_WAVES": "4"}),
+    ("spread, 2 waves", {"HB_GRID_WAVES": "2"}),
+    ("round-1 final build", {"HB_LIB_PATH": "profiles/ab_libs/lib_r1_final.so"}),
 ]
 def worker(name, log2n):
     sys.path.insert(0, ".")

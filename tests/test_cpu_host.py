@@ -428,3 +428,21 @@ def test_python_mirror_rejects_buffers_the_c_library_would_overrun():
         s.batch_energies(y, out=np.zeros((8, 3)))
     with pytest.raises(ValueError):
         s.batch_evolve(y, [0.0, 0.1, 0.2], out=np.zeros((2, 8, 4)))
+
+
+def test_evolve_rejects_a_zero_length_first_interval_for_the_adaptive_integrator():
+    """the reference's initial step is (ts[1] - ts[0]) / 100; zero makes GSL (and a GPU kernel) spin forever, so the
+    grid is rejected before anything is launched (argument validation needs no device)."""
+    s = hb.systems.builtin(hb.systems.DOUBLE_PENDULUM)
+    y = np.zeros((4, 4))
+    with pytest.raises(hb.HamiltonError) as ei:
+        s.batch_evolve(y, [0.0, 0.0, 0.1], integ=L.RKF45_GSL)
+    assert ei.value.status == L.ERR_INVALID
+    with pytest.raises(hb.HamiltonError) as ei:
+        s.batch_evolve(y, [0.0, 0.1, 0.05])
+    assert ei.value.status == L.ERR_INVALID
+    # misaligned array-of-Phases pointers are refused, not dereferenced (they would be a sticky device fault)
+    buf = np.zeros(4 * 4 + 1)
+    with pytest.raises(hb.HamiltonError) as ei:
+        s.batch_step(buf[1:].reshape(4, 4), 0.01)
+    assert ei.value.status == L.ERR_INVALID

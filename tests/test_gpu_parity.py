@@ -507,3 +507,25 @@ def test_largest_supported_system_n16(oracle_mod):
     assert bad == 0 and maxerr(s.batch_step(y, 0.01, 2, integ=L.RK4), yo) < 2 * TOL
     yo, bad = o.batch_step(y[:16], 1, 0.01, 1, threads=oracle_mod.max_threads())
     assert bad == 0 and maxerr(s.batch_step(y[:16], 0.01, 1, integ=L.RKF45_GSL), yo) < TOL
+
+
+def test_advice_r1_edge_cases(oracle_mod):
+    """ADVICE r1: (1) `stepHam r` with r <= 0 returns the Phase unchanged (hmatrix-gsl's `while (t < t1)` never runs);
+    (2) inertias around 1e-170 make the closed forms' determinant underflow although the mass matrix is perfectly
+    invertible (LAPACK's `inv` in the reference has no problem): the fast path's failed pivot test only sends the
+    trajectory to the scale-safe LDL^T of the slow path — finite velocities, no HB_FLAG_NOT_SPD."""
+    s = hb.systems.builtin(hb.systems.DOUBLE_PENDULUM)
+    y = random_phases("double_pendulum", 40)
+    for dt in (0.0, -0.01):
+        assert np.array_equal(s.batch_step(y, dt, 3, integ=L.RKF45_GSL), y)
+    tiny = hb.systems.builtin(hb.systems.DOUBLE_PENDULUM, [1e-170, 2e-170])
+    o = oracle_mod.OracleSystem.builtin(1, [1e-170, 2e-170])
+    yt = y.copy(); yt[:, 2:] *= 1e-170                      # momenta on the scale of the inertias: velocities are O(1)
+    fl = np.zeros(len(yt), np.int32)
+    c = tiny.batch_from_phase(yt, flags=fl)
+    assert not fl.any() and np.isfinite(c).all()
+    want = np.array([np.r_[r[:2], o.velocities(r[:2], r[2:])] for r in yt])
+    assert float(np.max(np.abs(c - want) / (1e-300 + np.abs(want)).clip(1e-3))) < 1e-9
+    dy = tiny.batch_ham_eqs(yt, flags=fl)
+    assert not fl.any() and np.isfinite(dy).all()
+    assert maxerr(dy[:, :2], o.batch_ham_eqs(yt)[:, :2]) < 1e-9
