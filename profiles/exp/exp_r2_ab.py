@@ -6,11 +6,7 @@ Timing: a CUDA graph of K one-step launches over a ring of 9 (in, out) buffer pa
 a graph of K launches ping-ponging between two buffers (a real stepping loop: L2-resident), and 16 steps fused per launch."""
 import os, subprocess, sys
 VARIANTS = [
-    ("default (tiles spread over CTAs, one wave)", {}),
-    ("contiguous tile map, one wave", {"HB_CONTIGUOUS": "1"}),
-    ("contiguous tile map, 2 waves (the round-1 shape)", {"HB_CONTIGUOUS": "1", "HB_GRID_WAVES": "2"}),
-    ("contiguous tile map, 4 waves", {"HB_CONTIGUOUS": "1", "HB_GRID_WAVES": "4"}),
-    ("spread, 2 waves", {"HB_GRID_WAVES": "2"}),
+    ("default", {}),
     ("round-1 final build", {"HB_LIB_PATH": "profiles/ab_libs/lib_r1_final.so"}),
 ]
 def worker(name, log2n):
