@@ -732,14 +732,41 @@ HB_DEV void hb_rhs_sm(HbCtx& cx, const double* prm, const double* w, const doubl
     hb_rhs<S, FAST>(cx, prm, w, in, k, flag);
   }
 }
+#ifndef HB_RK4_STAGE_LOOP
+#define HB_RK4_STAGE_LOOP 1   // large systems: the four stages are ONE loop around ONE copy of the RHS (instruction cache, see below)
+#endif
+// The RHS of a large system is thousands of straight-line instructions (chain (24,12): 1,600 = 26 KB).  Inlined four times the
+// step body is 104 KB — more than the 32 KB instruction cache level next to the SM can hold — and with two warps per
+// scheduler at different places of it every warp waits for instruction fetches (ncu: stall_no_instruction 1.09 cycles per
+// issue, profiles/r2l).  The stages therefore run as a loop (never unrolled) whose epilogue is selected by the
+// warp-uniform stage index; every sum is the same fma as in the unrolled form (fma(1, k, 0) == k, fma(1, k, acc) == acc + k),
+// so the results are bit-identical to it.
 template <class S, bool FAST>
 HB_DEV void hb_rk4_step_sm(HbCtx& cx, const double* prm, const double* w, double* sm, double dt, double h6, int& flag) {
   constexpr int D = 2 * S::N, B = HB_BLOCK_OF(S::N);
   double* ys = sm + threadIdx.x;            // y[c]   = ys[c * B]
   double* as = ys + D * B;                  // acc[c]
   double* ts = as + D * B;                  // yt[c]
-  double k[D];
   const double hh = 0.5 * dt;
+#if HB_RK4_STAGE_LOOP
+#pragma unroll 1
+  for (int st = 0; st < 4; st++) {
+    double k[D];
+    hb_rhs_sm<S, FAST>(cx, prm, w, st == 0 ? ys : ts, k, flag);
+    if (st == 0) {
+#pragma unroll
+      for (int c = 0; c < D; c++) { as[c * B] = k[c]; ts[c * B] = fma(hh, k[c], ys[c * B]); }
+    } else if (st < 3) {
+      const double cs = st == 1 ? hh : dt;
+#pragma unroll
+      for (int c = 0; c < D; c++) { as[c * B] = fma(2.0, k[c], as[c * B]); ts[c * B] = fma(cs, k[c], ys[c * B]); }
+    } else {
+#pragma unroll
+      for (int c = 0; c < D; c++) ys[c * B] = fma(h6, as[c * B] + k[c], ys[c * B]);
+    }
+  }
+#else
+  double k[D];
   hb_rhs_sm<S, FAST>(cx, prm, w, ys, k, flag);
 #pragma unroll
   for (int c = 0; c < D; c++) { as[c * B] = k[c]; ts[c * B] = fma(hh, k[c], ys[c * B]); }
@@ -752,6 +779,7 @@ HB_DEV void hb_rk4_step_sm(HbCtx& cx, const double* prm, const double* w, double
   hb_rhs_sm<S, FAST>(cx, prm, w, ts, k, flag);
 #pragma unroll
   for (int c = 0; c < D; c++) ys[c * B] = fma(h6, as[c * B] + k[c], ys[c * B]);
+#endif
 }
 
 // GSL-semantics adaptive RKF45 — what the reference's stepHam/evolveHam actually run
@@ -994,7 +1022,17 @@ HB_DEV void hb_traj_evolve(const HbKArgs& a, I i, const double* yin, const doubl
     } else {
       const double h = (tk - t) / a.substeps;
       const double h6 = h / 6.0;
-      for (int s = 0; s < a.substeps; s++) hb_rk4_step<S, FAST>(cx, a.prm, w, y, h, h6, 0.5 * h, flag);
+      if constexpr (D >= 16) {   // large systems: RK vectors in shared memory, stages as a loop (see hb_rk4_step_sm)
+        constexpr int B = HB_BLOCK_OF(S::N);
+        double* sm = hb_rk_smem<D>();
+#pragma unroll
+        for (int c = 0; c < D; c++) sm[c * B + threadIdx.x] = y[c];
+        for (int s = 0; s < a.substeps; s++) hb_rk4_step_sm<S, FAST>(cx, a.prm, w, sm, h, h6, flag);
+#pragma unroll
+        for (int c = 0; c < D; c++) y[c] = sm[c * B + threadIdx.x];
+      } else {
+        for (int s = 0; s < a.substeps; s++) hb_rk4_step<S, FAST>(cx, a.prm, w, y, h, h6, 0.5 * h, flag);
+      }
       t = tk;
     }
     if (FAST && hb_retry(cx)) return;   // rows written so far are rewritten by the slow retry (out never aliases in)

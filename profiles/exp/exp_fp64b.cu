@@ -1,6 +1,7 @@
 // Does a DFMA with three REGISTER operands still issue every 2 clocks per scheduler?  8 warps/SMSP, 8 chains per thread.
 //   A: x = fma(x, const, const)   B: x = fma(x, y_reg, const)   C: x = fma(x, y_reg, z_reg)   D: x = fma(y_reg, z_reg, x)
 //   F: x = fma(x, y_reg, y_reg) (3 reads, 2 distinct)   G: x = fma(x, x, z_reg)   H: x = fma(x, Y, Z), Y and Z the same two registers for all chains
+//   I, J: three distinct registers, one of them shared by 8 consecutive DFMAs (what ptxas marks .reuse in the LDL^T updates)
 //   E: C with 24 FFMA-pipe integer instructions mixed in per 64 DFMA (issue-slot pressure like the RK4 kernel: 77 per 224)
 // build: nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o exp_fp64b exp_fp64b.cu
 #include <cstdio>
@@ -25,6 +26,8 @@ __global__ void k(double* out, long long* cyc, const double* in, int iters, doub
         if (MODE == 5) x[c] = fma(x[c], y[c], y[c]);
         if (MODE == 6) x[c] = fma(x[c], x[c], z[c]);
         if (MODE == 7) x[c] = fma(x[c], y[0], z[0]);
+        if (MODE == 8) x[c] = fma(x[c], y[c], z[u & 1]);   // I: three distinct registers, the addend shared by 8 consecutive DFMAs (.reuse)
+        if (MODE == 9) x[c] = fma(y[c], z[u & 1], x[c]);   // J: the shared one is a multiplicand (the LDL^T update a_ij -= l_ik v_jk)
       }
       if (MODE == 4) {
 #pragma unroll
@@ -56,6 +59,6 @@ int main() {
   double* in; cudaMalloc(&in, 8 * 4096);
   double h[4096]; for (int i = 0; i < 4096; i++) h[i] = 1.0 + 1e-9 * (i % 97);
   cudaMemcpy(in, h, sizeof h, cudaMemcpyHostToDevice);
-  run<0>(sms, in); run<1>(sms, in); run<2>(sms, in); run<3>(sms, in); run<4>(sms, in); run<5>(sms, in); run<6>(sms, in); run<7>(sms, in);
+  run<0>(sms, in); run<1>(sms, in); run<2>(sms, in); run<3>(sms, in); run<4>(sms, in); run<5>(sms, in); run<6>(sms, in); run<7>(sms, in); run<8>(sms, in); run<9>(sms, in);
   return 0;
 }

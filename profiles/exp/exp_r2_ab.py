@@ -8,6 +8,7 @@ import os, subprocess, sys
 VARIANTS = [
     ("default", {}),
     ("round-1 final build", {"HB_LIB_PATH": "profiles/ab_libs/lib_r1_final.so"}),
+    ("round-2 build 8af0be2 (unrolled stages)", {"HB_LIB_PATH": "profiles/ab_libs/lib_r2_8af0be2.so"}),
 ]
 def worker(name, log2n):
     sys.path.insert(0, ".")
