@@ -810,8 +810,46 @@ HB_DEV void hb_rkf45_apply(HbCtx& cx, const double* prm, const double* w, double
                            double (&dydt_out)[2 * S::N], int& flag) {
   constexpr int D = 2 * S::N;
   typedef HbRkf45 T;
-  double k2[D], k3[D], k4[D], k5[D], k6[D], yt[D];
   const double h4 = T::ah0 * h;
+  if constexpr (D >= 16 && HB_RK4_STAGE_LOOP) {
+    // Large systems: ONE copy of the RHS inside a loop over the six evaluations (instruction cache, see hb_rk4_step_sm); the
+    // stage derivatives are addressed by the loop index, i.e. they live in local memory — where ptxas spills them anyway
+    // when the RHS needs every register.  Each case is the same fma chain as the straight-line form below: bit-identical.
+    double K[6][D], yt[D];   // K[0..4] = k2..k6, K[5] = dydt_out
+#pragma unroll 1
+    for (int st = 0; st < 6; st++) {
+      if (st == 0) {
+#pragma unroll
+        for (int c = 0; c < D; c++) yt[c] = fma(h4, k1[c], y[c]);
+      } else if (st == 1) {
+#pragma unroll
+        for (int c = 0; c < D; c++) yt[c] = fma(h, fma(T::b30, k1[c], T::b31 * K[0][c]), y[c]);
+      } else if (st == 2) {
+#pragma unroll
+        for (int c = 0; c < D; c++) yt[c] = fma(h, fma(T::b40, k1[c], fma(T::b41, K[0][c], T::b42 * K[1][c])), y[c]);
+      } else if (st == 3) {
+#pragma unroll
+        for (int c = 0; c < D; c++) yt[c] = fma(h, fma(T::b50, k1[c], fma(T::b51, K[0][c], fma(T::b52, K[1][c], T::b53 * K[2][c]))), y[c]);
+      } else if (st == 4) {
+#pragma unroll
+        for (int c = 0; c < D; c++)
+          yt[c] = fma(h, fma(T::b60, k1[c], fma(T::b61, K[0][c], fma(T::b62, K[1][c], fma(T::b63, K[2][c], T::b64 * K[3][c])))), y[c]);
+      } else {
+#pragma unroll
+        for (int c = 0; c < D; c++) {
+          const double di = fma(T::c1, k1[c], fma(T::c3, K[1][c], fma(T::c4, K[2][c], fma(T::c5, K[3][c], T::c6 * K[4][c]))));
+          y[c] = fma(h, di, y[c]);
+          yerr[c] = h * fma(T::e1, k1[c], fma(T::e3, K[1][c], fma(T::e4, K[2][c], fma(T::e5, K[3][c], T::e6 * K[4][c]))));
+          yt[c] = y[c];
+        }
+      }
+      hb_rhs<S, FAST>(cx, prm, w, yt, K[st], flag);
+    }
+#pragma unroll
+    for (int c = 0; c < D; c++) dydt_out[c] = K[5][c];
+    return;
+  }
+  double k2[D], k3[D], k4[D], k5[D], k6[D], yt[D];
 #pragma unroll
   for (int c = 0; c < D; c++) yt[c] = fma(h4, k1[c], y[c]);
   hb_rhs<S, FAST>(cx, prm, w, yt, k2, flag);
