@@ -49,13 +49,13 @@
 #define HB_BIG_N 8
 #define HB_DYN_DOUBLES(NCOORD, NE_) ((NCOORD) >= HB_BIG_N ? 3 * 2 * (NCOORD) + (NE_) : 0)
 // Dynamic shared memory of every kernel (hb_dsm), in this order — csrc/runtime.cpp dyn_smem_bytes() computes the same sizes:
-//   small systems (n < HB_BIG_N):  [ sin/cos table image: HB_TAB_BYTES, systems with sin/cos only ]  [ stage: 2 x DIN doubles per
+//   small systems (n < HB_BIG_N):  [ table image (sin/cos + 2^(j/64)): HB_TAB_BYTES, systems with sin/cos/exp only (Sys::TRIG) ]  [ stage: 2 x DIN doubles per
 //                                  thread, the cp.async landing zone of the thread's next Phase: stepping kernels of HEAVY
 //                                  systems only ]  [ xp ]
 //   large systems:                 [ RK vectors + parked values: HB_DYN_DOUBLES per thread ]  [ xp ]
 //   xp = DOUT doubles per thread, the warps' transpose buffers for host-memory stores; present only when a.layout == 2
 //   and DOUT is even and <= HB_WSTORE_MAXD.
-#define HB_TAB_BYTES 32896   // sizeof(HbTab) rounded up to 128 (static_assert below)
+#define HB_TAB_BYTES 33408   // sizeof(HbTab) rounded up to 128 (static_assert below)
 // Upper bound of the CTA size a kernel may be launched with (= __launch_bounds__).  A sweep of CTA sizes 128..384 x
 // resident waves 1..4 on B200 (profiles/r1d/sweep.txt) was flat within run-to-run noise, so it is the default size.
 #define HB_MAXBLOCK_OF(NCOORD) HB_BLOCK_OF(NCOORD)
@@ -306,7 +306,8 @@ static __device__ __constant__ double hb_kSC[5] = {
 
 // Shared-memory image of the table + the mbarrier its bulk copy completes on.
 struct HbTab {
-  double2 e[HB_SC_N];
+  double2 e[HB_SC_N];   // sin/cos
+  double x2[64];        // 2^(j/64) (hb_exp); directly behind e as in the global image, so that one bulk copy brings both
   unsigned long long bar;
 };
 static_assert(sizeof(HbTab) <= HB_TAB_BYTES, "HB_TAB_BYTES must hold the table image");
@@ -321,13 +322,16 @@ HB_DEV void hb_tab_issue(HbTab* tab) {
     const unsigned bar = (unsigned)__cvta_generic_to_shared(&tab->bar), dst = (unsigned)__cvta_generic_to_shared(tab->e);
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((unsigned)sizeof(tab->e)) : "memory");
+    constexpr unsigned bytes = sizeof(tab->e) + sizeof(tab->x2);
+    static_assert(sizeof(HbTabImage) == bytes && sizeof(HbTab) == bytes + 16, "shared image = global image (x2 directly behind e)");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(hb_kSinCosTab), "r"((unsigned)sizeof(tab->e)), "r"(bar) : "memory");
+                 ::"r"(dst), "l"(&hb_kTab), "r"(bytes), "r"(bar) : "memory");
   }
 #else
 #pragma unroll 1
   for (int t = threadIdx.x; t < HB_SC_N; t += blockDim.x) tab->e[t] = hb_kSinCosTab[t << (HB_SC_TAB_LOG2 - HB_SC_LOG2)];
+  if (threadIdx.x < 64) tab->x2[threadIdx.x] = hb_kTab.x2[threadIdx.x];
 #endif
   __syncthreads();   // the initialised mbarrier (or the staged entries) are visible to every thread of the CTA
 #else
@@ -380,6 +384,41 @@ HB_DEV void hb_sincos(HbCtx& cx, double x, double* sp, double* cp) {
 }
 template <bool FAST> HB_DEV double hb_sin(HbCtx& cx, double x) { double s, c; hb_sincos<FAST>(cx, x, &s, &c); return s; }
 template <bool FAST> HB_DEV double hb_cos(HbCtx& cx, double x) { double s, c; hb_sincos<FAST>(cx, x, &s, &c); return c; }
+
+// hb_exp<FAST>: the `exp` of user tapes (the logistic walls of the reference's room / spring / bezier examples,
+// app/Examples.hs:601-605).  x = (64 m + j) ln2/64 + r, |r| <= ln2/128:  exp x = 2^m * 2^(j/64) * e^r with 2^(j/64) from the
+// staged table and e^r - 1 = r + r^2 (1/2 + r/6 + r^2/24 + r^3/120) (truncation r^6/720 < 3.5e-17): 11 FP64 + 5 other
+// instructions against ~30 for libdevice's exp (degree-11 polynomial + range handling).  Two-term Cody-Waite reduction with
+// k * L1 exact (L1 has 19 trailing zero bits, |k| < 2^16).  Error < 2.5e-16 relative.  Domain |x| < 512 (result normal, no
+// overflow/denormal handling); outside (and NaN) only sets cx.oob and the trajectory is redone with libdevice's exp.
+template <bool FAST>
+HB_DEV double hb_exp(HbCtx& cx, double x) {
+  if constexpr (!FAST) {
+    return exp(x);
+  } else {
+    cx.oob |= (unsigned)!(fabs(x) < 512.0);
+    const double t = fma(x, HB_EXP_C0, 6755399441055744.0);   // 1.5 * 2^52: the low word of t is k = round(64 x / ln 2), two's complement
+    const int k = __double2loint(t);
+    double T;
+#ifdef HB_HOST_EMU
+    T = hb_kTab.x2[k & 63];
+#else
+    unsigned addr;
+    asm("{\n\t.reg .u32 j;\n\tand.b32 j, %1, 63;\n\tmad.lo.u32 %0, j, 8, %2;\n\t}" : "=r"(addr) : "r"(k), "r"(cx.tab_s + (unsigned)(sizeof(double2) * HB_SC_N)));
+    asm("ld.shared.f64 %0, [%1];" : "=d"(T) : "r"(addr));
+#endif
+    const double kf = t - 6755399441055744.0;
+    double r = fma(-kf, HB_EXP_L1, x);
+    r = fma(-kf, HB_EXP_L2, r);
+    const double z = r * r;
+    double q = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+    q = fma(r, q, 1.0 / 6.0);
+    q = fma(r, q, 0.5);
+    const double p = fma(z, q, r);
+    const double v = fma(T, p, T);
+    return __hiloint2double(__double2hiint(v) + ((k >> 6) << 20), __double2loint(v));   // * 2^m
+  }
+}
 
 // hb_rcp: 1/d for the mass-matrix pivots.  MUFU.RCP64H seed (relative error <= 2^-20, measured over 6e9 operands:
 // profiles/r1c/exp_rcp.txt) + ONE cubically convergent step x (1 + e + e^2), e = 1 - d x: 3 dependent DFMA, result

@@ -42,7 +42,7 @@ static const char* const KERNEL_KINDS[K_COUNT] = {"step_rk4", "step_rkf45", "evo
 #define HB_WSTORE_MAXD 8   // must match engine/hb_engine.cuh
 #define HB_DYN_DOUBLES(NCOORD, NE_) ((NCOORD) >= HB_BIG_N ? 3 * 2 * (NCOORD) + (NE_) : 0)
 #define HB_MAXBLOCK_OF(NCOORD) HB_BLOCK_OF(NCOORD)
-#define HB_TAB_BYTES 32896   // must match engine/hb_engine.cuh
+#define HB_TAB_BYTES 33408   // must match engine/hb_engine.cuh
 #define HB_MAX_LAUNCH_N ((int64_t)0x7C000000)   // 2^31 - 2^26: i + (trajectories per round) stays below 2^32 in the kernels
 
 // from aot_kernels.cu
@@ -239,7 +239,7 @@ struct hb_system {
   int dyn_doubles = 0;                 // dynamic shared memory per thread (doubles) every kernel of this system is launched with
   int rhs_cost = 0;                    // system compiler's cost model of one hamEqs evaluation
   bool heavy = false;                  // Sys::HEAVY: one RK4 step is issue-bound, not HBM-bound (launch-shape heuristic)
-  bool trig = false;                   // Sys::TRIG: the kernels stage the sin/cos table image in dynamic shared memory
+  bool trig = false;                   // Sys::TRIG (sin / cos / exp on the tapes): the kernels stage the table image in dynamic shared memory
   double intensity = 0;                // issue clocks / HBM clocks of one RK4 step (system compiler's estimate)
   std::string source;                  // generated Sys struct
   // JIT: small systems compile all kernels in one NVRTC program at creation (cubins[K_COUNT] shared slot 0);

@@ -87,7 +87,7 @@ struct Emitter {
           os << "    const double t" << id << " = (double)((" << A() << " > 0.0) - (" << A() << " < 0.0));\n";
           break;
         case Op::Sqrt: fn1("sqrt"); break;
-        case Op::Exp: fn1("exp"); break;
+        case Op::Exp: os << "    const double t" << id << " = hb_exp<FAST>(cx, " << A() << ");\n"; break;
         case Op::Log: fn1("log"); break;
         case Op::Sin: case Op::Cos: {
           auto p = sc[n.a];
@@ -454,7 +454,7 @@ bool generate_system(const SystemSpec& spec, const std::string& name, GeneratedS
   os << "  static constexpr bool SYMH = " << (SH.ok ? "true" : "false") << ";\n";
   os << "  static constexpr int NE = " << (SH.ok ? (int)SH.carried.size() : 0) << ";\n";
   bool trig = false;
-  for (const Node& nd : G.nodes) trig = trig || nd.op == Op::Sin || nd.op == Op::Cos;
+  for (const Node& nd : G.nodes) trig = trig || nd.op == Op::Sin || nd.op == Op::Cos || nd.op == Op::Exp;   // needs the staged table image
   os << "  static constexpr bool TRIG = " << (trig ? "true" : "false") << ";\n";
   // HEAVY: is one RK4 step of a trajectory issue-bound or HBM-bound?  Issue clocks per tile of 32 trajectories and SM:
   // (2 clk x (4 RHS x (cost model + solve) + 14 n of RK4 algebra) + 60 of bookkeeping) / 4 schedulers; HBM clocks per tile and

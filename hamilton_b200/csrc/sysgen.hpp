@@ -32,7 +32,7 @@ struct GeneratedSystem {
   int n_nodes = 0;       // size of the derivative DAG (diagnostics)
   int ne = 0;            // values hpre hands to hpost (Sys::NE; 0 when the direct contraction is used)
   int rhs_cost = 0;      // cost model of one hamEqs evaluation in the emitted form (arithmetic ops; transcendental = 14), without the solve
-  bool trig = false;     // uses sin / cos (Sys::TRIG): its kernels stage the table image
+  bool trig = false;     // uses sin / cos / exp (Sys::TRIG): its kernels stage the table image
   double intensity = 0;  // issue clocks / HBM clocks of one RK4 step per tile (the estimate behind `heavy`)
   bool heavy = false;    // one RK4 step costs clearly more issue time than its 32n bytes cost HBM time (Sys::HEAVY)
 };

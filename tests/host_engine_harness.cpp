@@ -23,6 +23,7 @@ struct HbEmuDim { unsigned x, y, z; };
 static HbEmuDim threadIdx = {0, 0, 0}, blockIdx = {0, 0, 0}, blockDim = {128, 1, 1}, gridDim = {1, 1, 1};
 static inline int __double2hiint(double v) { long long b; std::memcpy(&b, &v, 8); return (int)(b >> 32); }
 static inline int __double2loint(double v) { long long b; std::memcpy(&b, &v, 8); return (int)(b & 0xffffffffLL); }
+static inline double __hiloint2double(int hi, int lo) { const unsigned long long b = ((unsigned long long)(unsigned)hi << 32) | (unsigned)lo; double v; std::memcpy(&v, &b, 8); return v; }
 static inline unsigned __activemask() { return 1u; }
 static inline void __syncwarp() {}
 static inline void __syncthreads() {}
@@ -128,6 +129,7 @@ extern "C" int config_maps(const double* prm, const double* q, const double* v, 
 // primitives
 extern "C" int sincos_fast(double x, double* s, double* c) { HbCtx cx = ctx(); hb_sincos<true>(cx, x, s, c); return cx.oob ? 1 : 0; }
 extern "C" double rcp_fast(double d) { return hb_rcp(d); }
+extern "C" int exp_fast(double x, double* e) { HbCtx cx = ctx(); *e = hb_exp<true>(cx, x); return cx.oob ? 1 : 0; }
 template <int NN> static int spd(const double* A_packed, const double* b, double* x) {
   double A[NN * (NN + 1) / 2];
   for (int i = 0; i < NN * (NN + 1) / 2; i++) A[i] = A_packed[i];

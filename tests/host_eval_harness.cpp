@@ -11,6 +11,7 @@ template <bool FAST> static inline void hb_sincos(HbCtx&, double x, double* s, d
 template <bool FAST> static inline double hb_sin(HbCtx&, double x) { return std::sin(x); }
 template <bool FAST> static inline double hb_cos(HbCtx&, double x) { return std::cos(x); }
 template <bool FAST> static inline double hb_recip(HbCtx&, double x) { return 1.0 / x; }
+template <bool FAST> static inline double hb_exp(HbCtx&, double x) { return std::exp(x); }
 using std::exp; using std::log; using std::sqrt; using std::pow; using std::fabs; using std::tan; using std::atan2;
 using std::asin; using std::acos; using std::atan; using std::sinh; using std::cosh; using std::tanh;
 using std::asinh; using std::acosh; using std::atanh;

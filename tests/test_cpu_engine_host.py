@@ -199,6 +199,29 @@ def test_fast_sincos_on_host():
         assert lib.sincos_fast(x, C.byref(s), C.byref(c)) != 0, x
 
 
+def test_fast_exp_on_host():
+    """hb_exp<FAST>: 64-entry 2^(j/64) table, two-term Cody-Waite reduction, degree-5 polynomial: relative error < 2.5e-16
+    against a 60-digit reference over the whole domain |x| < 512; everything else (huge, inf, nan) flags `oob`."""
+    import mpmath as mp
+    mp.mp.dps = 40
+    lib, _, _ = harness("pendulum")
+    lib.exp_fast.argtypes = [C.c_double, _dp]
+    rng = np.random.default_rng(13)
+    ln2_64 = np.log(2.0) / 64
+    xs = np.r_[rng.uniform(-1, 1, 6000), rng.uniform(-40, 40, 6000), rng.uniform(-511.9, 511.9, 6000), rng.uniform(-1e-8, 1e-8, 500),
+               np.arange(-3000, 3001) * ln2_64, (np.arange(-3000, 3001) + 0.5) * ln2_64,   # table nodes and the reduction's break points
+               [0.0, -0.0, 1e-300, -1e-300, 511.999, -511.999, np.log(2.0), -np.log(2.0)]]
+    e = C.c_double()
+    worst = 0.0
+    for x in xs:
+        assert lib.exp_fast(float(x), C.byref(e)) == 0, x
+        ref = mp.exp(mp.mpf(float(x)))
+        worst = max(worst, float(abs(mp.mpf(e.value) - ref) / ref))
+    assert worst < 2.5e-16, worst
+    for x in (512.0, -512.0, 600.0, -1e9, 1e300, float("inf"), float("-inf"), float("nan")):
+        assert lib.exp_fast(x, C.byref(e)) != 0, x
+
+
 def test_fast_reciprocal_on_host():
     """hb_rcp: 20-bit seed (emulated MUFU.RCP64H) + one cubic step: within 1 ulp over the exponent range the solves see."""
     lib, _, _ = harness("pendulum")
