@@ -495,16 +495,30 @@ LaunchShape pick_shape(const hb_system* s, int kid, const void* fn, long long n_
   // CTAs of the second wave go to whichever SM frees up first: dynamic balance, 6 % against one static wave, profiles/r2n)
   if (s->n >= HB_BIG_N) { LaunchShape sh = one_wave(HB_BLOCK_OF(s->n)); const long long need = (n_traj + sh.block - 1) / sh.block; sh.grid = std::min<long long>(need, 2 * sh.grid); sh.contiguous = 1; return sh; }
   if (block_env) return one_wave(block_env);
-  // HBM-bound launches (light systems, the one-evaluation kernels): what counts is bytes in flight — full occupancy, small CTAs.
-  // The most HBM-bound of them (two-body, 1-D spring: issue/HBM estimate below 1.2; the one-evaluation kernels) stream best as
-  // FOUR waves with the contiguous tile map (two-body 23.1 us against 25.1 for one spread wave, 1-D spring 10.9 against 11.4);
-  // the pendulum (1.4) is fastest as one spread wave (14.8 against 17.0) — profiles/r2s.
+  // HBM-bound launches (light systems, the one-evaluation kernels): what counts is bytes in flight and how often the 32 KB
+  // table image is staged (once per CTA).  Measured per system over CTA sizes 128/256/512 x 1/2/4 waves x both tile maps
+  // (profiles/r2x, r2y; round-2 rule before that: 128 threads, four waves, profiles/r2s):
+  //   one-evaluation kernels (hamEqs, toPhase, ...): 512-thread CTAs with the contiguous tile map everywhere; ONE wave for the
+  //     small table-staging systems (pendulum hamEqs 14.2 -> 10.5 us = 0.98 of the measured HBM peak, double pendulum 13.7 ->
+  //     12.3, room 14.3 -> 11.3), FOUR waves for records of >= 6 doubles and for systems without a table (triple pendulum
+  //     22.0 -> 19.4, two-body 25.3 -> 24.0, 1-D spring 10.9 -> 10.4);
+  //   stepping kernels: a light system that stages the table (pendulum, 1.4) runs best as one spread wave of 512-thread
+  //     CTAs (14.6 -> 13.6 us); the most HBM-bound ones without a table (two-body, 1-D spring: estimate below 1.2) as four
+  //     contiguous waves of 128-thread CTAs (two-body 23.1 us against 25.1 for one spread wave, 1-D spring 10.9 against 11.4).
   if (!heavy) {
-    LaunchShape sh = one_wave(128);
-    if (waves_env <= 0 && (!stepping_kernel(kid) || s->intensity < 1.2)) {
+    const bool one_eval = !stepping_kernel(kid);
+    const bool big_cta = one_eval || s->trig;
+    LaunchShape sh = one_wave(big_cta ? 512 : 128);
+    if (waves_env <= 0) {
       const long long need = (n_traj + sh.block - 1) / sh.block;
-      sh.grid = std::min<long long>(need, 4 * sh.grid);
-      sh.contiguous = 1;
+      if (one_eval) {
+        const int waves = (s->trig && in_d < 6) ? 1 : 4;
+        sh.grid = std::min<long long>(need, waves * sh.grid);
+        sh.contiguous = 1;
+      } else if (!s->trig && s->intensity < 1.2) {
+        sh.grid = std::min<long long>(need, 4 * sh.grid);
+        sh.contiguous = 1;
+      }
     }
     return sh;
   }
