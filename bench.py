@@ -493,6 +493,13 @@ def main():
     ca, cb = ring_in[0].clone(), ring_out[0]
     chain_ms, _, _, _, _ = H.time_launches(lambda i: sysm.batch_step(ca if i % 2 == 0 else cb, DT, 1, integ=L.RK4, out=cb if i % 2 == 0 else ca), K)
 
+    # the path's central function on its own: ONE hamEqs evaluation per trajectory per launch (hb_batch_ham_eqs, src/Numeric/Hamilton.hs:370-387)
+    # over the same ring of batches — the HBM-bound kernel of the path, against the same roofline
+    for i in range(3):
+        sysm.batch_ham_eqs(ring_in[i % RING], out=ring_out[i % RING])
+    hameqs_ms, _, _, _, _ = H.time_launches(lambda i: sysm.batch_ham_eqs(ring_in[i % RING], out=ring_out[i % RING]), K)
+    hameqs_ms = H.reduce_max(hameqs_ms)
+
     # ---------------- final collection: one NCCL all-gather of the final Phases ----------------
     gather_ms = 0.0
     if world > 1:
@@ -603,6 +610,9 @@ def main():
                       "note": "explanation only: K dependent one-step launches ping-ponging between two buffers (32 MiB state stays in L2)"},
             "burst": {"value": world * N / (burst_ms * 1e-3), "unit": "steps/s", "ms_per_step": burst_ms, "launches": K,
                       "note": "explanation only: the K = --steps launches alone (a sub-10-ms region, as round 1 timed it); `value` is the >= 100 ms region, which on this part runs into the power cap (clocks.reasons) when every launch streams 64 MiB through HBM"},
+            "ham_eqs": {"value": world * N / (hameqs_ms * 1e-3), "unit": "hamEqs evaluations/s", "ms_per_launch": hameqs_ms,
+                        "roofline": roofline_obj(2, N, hameqs_ms, "hbk_double_pendulum_dflt_ham_eqs"),
+                        "note": "explanation only: one hamEqs evaluation per trajectory per launch (hb_batch_ham_eqs), the HBM-bound kernel of the path; same batches, same ring"},
             "configs": configs,
         }
         if world > 1:

@@ -11,6 +11,8 @@ for b in (128, 256, 512):
         for c in (0, 1):
             if not FULL and not (c == 1 and (w, b) in ((1, 128), (4, 128), (1, 256), (2, 256), (1, 512), (2, 512), (4, 512))) and not (c == 0 and (w, b) == (1, 512)): continue
             VARIANTS.append(("block %d, %d wave(s), %s" % (b, w, "contiguous" if c else "spread"), {"HB_BLOCK": str(b), "HB_GRID_WAVES": str(w), "HB_CONTIGUOUS": str(c)}))
+if os.environ.get("HB_SWEEP_WAVES"):   # large systems: only the number of waves is a knob (grid = min(tiles, 2 x waves x resident CTAs))
+    VARIANTS = [("default", {})] + [("HB_GRID_WAVES=%s" % w, {"HB_GRID_WAVES": w}) for w in os.environ["HB_SWEEP_WAVES"].split(",")]
 def worker(name, log2n):
     sys.path.insert(0, ".")
     import torch
@@ -22,7 +24,7 @@ def worker(name, log2n):
     ring = max(2, int(600e6 // (2 * N * 2 * s.n * 8)) + 1)
     ins = [s.batch_init_random(7 + r, 0, N, lo, hi) for r in range(ring)]
     outs = [torch.empty_like(b) for b in ins]
-    K = 200
+    K = int(os.environ.get('HB_SWEEP_K', '200'))
     def graph_time(body):
         g = torch.cuda.CUDAGraph()
         st = torch.cuda.Stream()
