@@ -481,6 +481,9 @@ HB_DEV void hb_mass(const double* wJ, const double* Jv, double* A) {
   });
 }
 
+#ifndef HB_SOLVE_COLS
+#define HB_SOLVE_COLS 1   // LDL^T and substitutions in column (axpy) order; 0: row (dot-product) order
+#endif
 // (A right-looking ordering of the LDL^T updates — runs of DFMAs sharing their first operand, for the operand-reuse cache —
 // measured no different on the 12 x 12 chain: profiles/r2l/ab_chain12_ldlt.txt.)
 // Solve A x = b for the packed SPD mass matrix; A is destroyed.  Replaces the reference's explicit
@@ -546,6 +549,28 @@ HB_DEV void hb_spd_solve_v(double* A, const BV b, double* x, int& minpiv) {
   } else {
     // LDL^T, fully unrolled by compile-time recursion (a rolled loop would index A dynamically and push it to local memory)
     double invd[N];
+#if HB_SOLVE_COLS
+    // Column-oriented ("right-looking", axpy) order: as soon as column k is final every element it touches is updated, so
+    // consecutive DFMAs write DIFFERENT accumulators and share one operand (operand-reuse cache).  The row-oriented (dot
+    // product) order below has the same dependency graph per element, but ptxas emits it as written: runs of DFMAs on ONE
+    // accumulator, 8 clocks apart — with two warps per scheduler (large systems) a third of all warp samples of the chain's
+    // step waited on those chains (profiles/r2u).  The factorisation and the forward substitution do per element exactly the
+    // operations of the row-oriented form in the same order (bit-identical); the backward substitution accumulates in
+    // descending instead of ascending column order (last-bit differences).
+    hb_static_for<0, N>([&](auto kt) {
+      HB_IDX(k, kt);
+      const double d = A[hb_tri(k, k)];
+      hb_piv(minpiv, d);
+      const double id = hb_rcp(d);
+      invd[k] = id;
+      hb_static_for<k + 1, N>([&](auto it) { HB_IDX(i, it); A[hb_tri(i, k)] *= id; });   // column k: t_ik -> L_ik
+      hb_static_for<k + 1, N>([&](auto jt) {   // column j of the trailing matrix: A_ij -= L_ik (L_jk d_k), i >= j
+        HB_IDX(j, jt);
+        const double v = A[hb_tri(j, k)] * d;                     // L_jk d_k  (as the row form computes it)
+        hb_static_for<j, N>([&](auto it) { HB_IDX(i, it); A[hb_tri(i, j)] = fma(-A[hb_tri(i, k)], v, A[hb_tri(i, j)]); });
+      });
+    });
+#else
     hb_static_for<0, N>([&](auto jt) {
       HB_IDX(j, jt);
       double v[j > 0 ? j : 1];
@@ -566,6 +591,22 @@ HB_DEV void hb_spd_solve_v(double* A, const BV b, double* x, int& minpiv) {
         A[hb_tri(i, j)] = t * id;
       });
     });
+#endif
+#if HB_SOLVE_COLS
+#pragma unroll
+    for (int j = 0; j < N; j++) x[j] = b(j);
+    hb_static_for<0, N>([&](auto jt) {   // L y = b: y_j is final, every later row takes its share of it
+      HB_IDX(j, jt);
+      hb_static_for<j + 1, N>([&](auto it) { HB_IDX(i, it); x[i] = fma(-A[hb_tri(i, j)], x[j], x[i]); });
+    });
+#pragma unroll
+    for (int j = 0; j < N; j++) x[j] *= invd[j];   // D z = y
+    hb_static_for<0, N>([&](auto rt) {   // L^T x = z
+      HB_IDX(r, rt);
+      constexpr int j = N - 1 - r;
+      hb_static_for<0, j>([&](auto it) { HB_IDX(i, it); x[i] = fma(-A[hb_tri(j, i)], x[j], x[i]); });
+    });
+#else
     hb_static_for<0, N>([&](auto jt) {   // L y = b
       HB_IDX(j, jt);
       double t = b(j);
@@ -581,6 +622,7 @@ HB_DEV void hb_spd_solve_v(double* A, const BV b, double* x, int& minpiv) {
       hb_static_for<j + 1, N>([&](auto kt) { HB_IDX(k, kt); t = fma(-A[hb_tri(k, j)], x[k], t); });
       x[j] = t;
     });
+#endif
   }
 }
 

@@ -10,6 +10,8 @@ VARIANTS = [
     ("round-1 final build", {"HB_LIB_PATH": "profiles/ab_libs/lib_r1_final.so"}),
     ("round-2 build 8af0be2 (unrolled stages)", {"HB_LIB_PATH": "profiles/ab_libs/lib_r2_8af0be2.so"}),
 ]
+for kv in filter(None, os.environ.get("HB_AB_LIBS", "").split(",")):   # extra saved builds: HB_AB_LIBS=label=path,label=path
+    VARIANTS.append((kv.split("=")[0], {"HB_LIB_PATH": kv.split("=", 1)[1]}))
 def worker(name, log2n):
     sys.path.insert(0, ".")
     import torch
