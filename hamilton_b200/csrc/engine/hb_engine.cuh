@@ -288,18 +288,20 @@ HB_DEV void hb_ctx_reset(HbCtx& cx) { cx.oob = 0; cx.minpiv = 0x7fffffff; }
 // The constants sit in the constant bank so that they are DIRECT operands of the FP64 instructions (written as literals
 // ptxas rebuilds each one in a register pair per trajectory: 18 extra issue slots per RK4 step of the double pendulum).
 #if HB_SC_LOG2 == 11
-static __device__ __constant__ double hb_kSC[5] = {
+static __device__ __constant__ double hb_kSC[6] = {
     325.94932345220167,        // 0  1024 / pi
     0.0030679615757712823,     // 1  pi / 1024 (fp64)
     1.195944139792337e-19,     // 2  pi / 1024 - fp64(pi / 1024)
     -0.16666664960671299,      // 3  S1' = -1/6 + 0.87 zmax / 120: minimax for sin r = r + r^3 S1' over |r| <= pi/2048
-    0.0};
+    0.0,
+    HB_SC_MAGIC};              // 5  (as a literal ptxas rebuilds the magic constant in a register pair twice per trajectory)
 #elif HB_SC_LOG2 == 9
-static __device__ __constant__ double hb_kSC[5] = {
+static __device__ __constant__ double hb_kSC[6] = {
     81.48733086305042,         // 0  256 / pi
     0.01227184630308513,       // 1  pi / 256 (fp64)
     4.783776559169348e-19,     // 2  pi / 256 - fp64(pi / 256)
-    -1.0 / 6.0, 1.0 / 120.0};  // 3, 4  sin r = r + r^3 (S1 + z S2), |r| <= pi/512: r^7/5040 < 1e-17 r
+    -1.0 / 6.0, 1.0 / 120.0,   // 3, 4  sin r = r + r^3 (S1 + z S2), |r| <= pi/512: r^7/5040 < 1e-17 r
+    HB_SC_MAGIC};
 #else
 #error "HB_SC_LOG2 must be 9 or 11"
 #endif
@@ -355,7 +357,7 @@ HB_DEV void hb_sincos(HbCtx& cx, double x, double* sp, double* cp) {
   if constexpr (!FAST) {
     sincos(x, sp, cp);
   } else {
-    const double t = fma(x, hb_kSC[0], HB_SC_MAGIC);
+    const double t = fma(x, hb_kSC[0], hb_kSC[5]);
     cx.oob |= (unsigned)__double2hiint(t) ^ 0x43380000u;   // 0 <=> -2^31 <= k < 2^31 (inf/nan/huge arguments land elsewhere)
     double2 sc;   // one LDS.128 with a 32-bit shared address (no generic->shared conversion in the loop)
 #ifdef HB_HOST_EMU
@@ -365,7 +367,7 @@ HB_DEV void hb_sincos(HbCtx& cx, double x, double* sp, double* cp) {
     asm("{\n\t.reg .u32 k;\n\tand.b32 k, %1, %2;\n\tmad.lo.u32 %0, k, 16, %3;\n\t}" : "=r"(addr) : "r"(__double2loint(t)), "n"(HB_SC_N - 1), "r"(cx.tab_s));
     asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(sc.x), "=d"(sc.y) : "r"(addr));
 #endif
-    const double kf = t - HB_SC_MAGIC;
+    const double kf = t - hb_kSC[5];
     double r = fma(-kf, hb_kSC[1], x);
 #if HB_SC_CW2
     r = fma(-kf, hb_kSC[2], r);

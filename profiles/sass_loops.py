@@ -1,5 +1,6 @@
 """Static SASS view of a kernel: every backward branch (loop) with its instruction mix, FP64 count and the issue clocks of
-the model measured in profiles/r2a (FP64 = 2 clk, 3 with three distinct register operands, everything else 1).
+the model measured in profiles/r2a and r2u (FP64 = 2 clk, 3 with three distinct register operands — 2.3 when one of them
+carries the .reuse flag, i.e. is the previous instruction's operand in the same slot —, LDS 2, everything else 1).
 usage: sass_loops.py <obj|cubin|so> <kernel> [--dump lo hi]"""
 import re, subprocess, sys
 from collections import Counter
@@ -19,14 +20,17 @@ def three_reg(t):
     regs = set(re.findall(r"\bR(\d+)\b", ops.split(',', 1)[1])) if ',' in ops else set()
     return len(regs) >= 3 and 'c[' not in ops
 def clocks(lo, hi, skip=()):
-    n = f = t3 = 0
+    n = f = t3 = t3r = lds = 0
     c = Counter()
     for a, t in ins:
         if lo <= a <= hi and not any(s0 <= a <= s1 for s0, s1 in skip):
             n += 1; c[opname(t)] += 1
             if fp64(t): f += 1
-            if three_reg(t): t3 += 1
-    return n, f, t3, c
+            if three_reg(t):
+                t3 += 1
+                if '.reuse' in t: t3r += 1
+            if opname(t) == 'LDS' and not t.startswith('@!PT'): lds += 1
+    return n, f, t3, c, t3r, lds
 if len(sys.argv) > 3 and sys.argv[3] == '--dump':
     lo, hi = int(sys.argv[4], 16), int(sys.argv[5], 16)
     for a, t in ins:
@@ -37,6 +41,6 @@ for a, t in ins:
     m = re.search(r"BRA(?:\.U)?\s+(?:!?U?P\d+,\s*)?(0x[0-9a-f]+)", t)
     if m and int(m.group(1), 16) < a and a - int(m.group(1), 16) > 64:
         lo = int(m.group(1), 16)
-        n, f, t3, c = clocks(lo, a)
-        print(f"  loop {hex(lo)}..{hex(a)}: {n} instr, {f} FP64 ({t3} three-register), issue clocks {n + f + t3};  " +
+        n, f, t3, c, t3r, lds = clocks(lo, a)
+        print(f"  loop {hex(lo)}..{hex(a)}: {n} instr, {f} FP64 ({t3} three-register, {t3r} of them .reuse), {lds} LDS, issue clocks {n + f + (t3 - t3r) + 0.3 * t3r + lds:.0f};  " +
               ", ".join(f"{k} {v}" for k, v in c.most_common(10)))
