@@ -294,7 +294,7 @@ static __device__ __constant__ double hb_kSC[6] = {
     1.195944139792337e-19,     // 2  pi / 1024 - fp64(pi / 1024)
     -0.16666664960671299,      // 3  S1' = -1/6 + 0.87 zmax / 120: minimax for sin r = r + r^3 S1' over |r| <= pi/2048
     0.0,
-    HB_SC_MAGIC};              // 5  (as a literal ptxas rebuilds the magic constant in a register pair twice per trajectory)
+    HB_SC_MAGIC};              // 5  (unused: see hb_sincos)
 #elif HB_SC_LOG2 == 9
 static __device__ __constant__ double hb_kSC[6] = {
     81.48733086305042,         // 0  256 / pi
@@ -357,7 +357,7 @@ HB_DEV void hb_sincos(HbCtx& cx, double x, double* sp, double* cp) {
   if constexpr (!FAST) {
     sincos(x, sp, cp);
   } else {
-    const double t = fma(x, hb_kSC[0], hb_kSC[5]);
+    const double t = fma(x, hb_kSC[0], HB_SC_MAGIC);   // literal on purpose: from the constant bank (hb_kSC[5]) ptxas loads it with an LDC per trajectory and the step is 1.2 % slower (profiles/r3c/ab_double_pendulum.txt)
     cx.oob |= (unsigned)__double2hiint(t) ^ 0x43380000u;   // 0 <=> -2^31 <= k < 2^31 (inf/nan/huge arguments land elsewhere)
     double2 sc;   // one LDS.128 with a 32-bit shared address (no generic->shared conversion in the loop)
 #ifdef HB_HOST_EMU
@@ -367,7 +367,7 @@ HB_DEV void hb_sincos(HbCtx& cx, double x, double* sp, double* cp) {
     asm("{\n\t.reg .u32 k;\n\tand.b32 k, %1, %2;\n\tmad.lo.u32 %0, k, 16, %3;\n\t}" : "=r"(addr) : "r"(__double2loint(t)), "n"(HB_SC_N - 1), "r"(cx.tab_s));
     asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(sc.x), "=d"(sc.y) : "r"(addr));
 #endif
-    const double kf = t - hb_kSC[5];
+    const double kf = t - HB_SC_MAGIC;
     double r = fma(-kf, hb_kSC[1], x);
 #if HB_SC_CW2
     r = fma(-kf, hb_kSC[2], r);
