@@ -17,7 +17,7 @@ gaps between consecutive replays of one executable graph, which are launch plumb
   roofline   HBM roofline of the dominant kernel (hbk_double_pendulum_dflt_step_rk4) + the instruction-issue view that binds it.
   cpu_baseline   the CPU oracle (restatement of the reference algorithm) on this box's host cores, the SAME 1,048,576 batch.
   configs    BASELINE configs[2], [3], [4] measured the same way (`--config 3|4|5` makes one of them the whole run):
-             "3" 2,097,152 pendulums (System 2 1) + 2,097,152 two-body orbits (System 4 2) on two streams,
+             "3" 2,097,152 pendulums (System 2 1) + 2,097,152 two-body orbits (System 4 2) (two streams or one, whichever is faster),
              "4" triple pendulum (System 6 3), 8,388,608 initial conditions split over the N GPUs (STRONG scaling), 1000 steps,
                  one NCCL all-gather of the final Phases INSIDE the timed region,
              "5" 12-link chain (System 24 12), batch 262,144.
@@ -325,17 +325,23 @@ def bench_simple(H, name, N, K, kernel):
 
 
 def bench_config3(H, K):
-    """2,097,152 pendulums (System 2 1) + 2,097,152 two-body orbits (System 4 2): two kernels on two streams per step."""
+    """2,097,152 pendulums (System 2 1) + 2,097,152 two-body orbits (System 4 2): two kernels per step (independent chains on two streams, or alternating on one)."""
     torch, L = H.torch, H.L
     Np = 1 << 21
     sp, pin, pout = H.ring_for("pendulum", Np, min_bytes=288 << 20)
     st, tin, tout = H.ring_for("two_body", Np, min_bytes=288 << 20)
     s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
 
-    def run(k):
-        """k steps of both batches: the two systems are independent, so each runs its own chain of k launches on its own stream
-        (forked once, joined once) and the kernels of the two chains overlap freely."""
+    def run(k, two_streams):
+        """k steps of both batches.  two_streams: the two systems are independent, so each runs its own chain of k launches on
+        its own stream (forked once, joined once) and the kernels of the two chains overlap freely; otherwise the 2k launches
+        alternate on ONE stream (each kernel has the whole GPU, the next one's prologue overlaps its tail through PDL)."""
         cur = torch.cuda.current_stream()
+        if not two_streams:
+            for i in range(k):
+                sp.batch_step(pin[i % len(pin)], DT, 1, integ=L.RK4, out=pout[i % len(pin)])
+                st.batch_step(tin[i % len(tin)], DT, 1, integ=L.RK4, out=tout[i % len(tin)])
+            return
         s1.wait_stream(cur); s2.wait_stream(cur)
         with torch.cuda.stream(s1):
             for i in range(k):
@@ -344,27 +350,33 @@ def bench_config3(H, K):
             for i in range(k):
                 st.batch_step(tin[i % len(tin)], DT, 1, integ=L.RK4, out=tout[i % len(tin)])
         cur.wait_stream(s1); cur.wait_stream(s2)
-    run(3)
-    H.barrier()
-    small, how = H.capture([lambda: run(K)])
-    small(); H.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(); small(); e1.record()
-    H.barrier()
-    R = max(1, int(math.ceil(MIN_REGION_MS / max(e0.elapsed_time(e1), 1e-3))))
-    nl = K * R
-    big, how = H.capture([lambda: run(nl)]) if R > 1 else (small, how)
-    big(); H.barrier()
-    e0.record(); big(); e1.record()
-    H.barrier()
-    per = e0.elapsed_time(e1) / nl
+
+    def timed(two_streams):
+        run(3, two_streams)
+        H.barrier()
+        small, how = H.capture([lambda: run(K, two_streams)])
+        small(); H.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); small(); e1.record()
+        H.barrier()
+        R = max(1, int(math.ceil(MIN_REGION_MS / max(e0.elapsed_time(e1), 1e-3))))
+        nl = K * R
+        big, how = H.capture([lambda: run(nl, two_streams)]) if R > 1 else (small, how)
+        big(); H.barrier()
+        e0.record(); big(); e1.record()
+        H.barrier()
+        return e0.elapsed_time(e1) / nl, nl, how
+    per2, nl2, how2 = timed(True)
+    per1, nl1, how1 = timed(False)
+    per, nl, how, mode = (per2, nl2, how2, "two streams") if per2 <= per1 else (per1, nl1, how1, "one stream, alternating")
     algo = Np * 32 + Np * 64
     peak, peak_src = peaks()
     ach = algo / (per * 1e-3) / 1e9
-    return {"workload": "2,097,152 pendulums (System 2 1) + 2,097,152 two-body orbits (System 4 2), mixed batch 4,194,304, two streams (BASELINE configs[2])",
-            "value": 2 * Np / (per * 1e-3), "unit": "steps/s", "ms_per_step": per, "launches_timed": 2 * nl, "launch": how,
+    return {"workload": "2,097,152 pendulums (System 2 1) + 2,097,152 two-body orbits (System 4 2), mixed batch 4,194,304 (BASELINE configs[2])",
+            "value": 2 * Np / (per * 1e-3), "unit": "steps/s", "ms_per_step": per, "launches_timed": 2 * nl, "launch": how, "mode": mode,
+            "ms_per_step_two_streams": per2, "ms_per_step_one_stream": per1,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
-                         "kernel": "hbk_pendulum_step_rk4 + hbk_two_body_dflt_step_rk4 (concurrent)", "algorithmic_bytes_per_launch": algo}}
+                         "kernel": "hbk_pendulum_step_rk4 + hbk_two_body_dflt_step_rk4 (" + mode + ")", "algorithmic_bytes_per_launch": algo}}
 
 
 def bench_config4(H, steps=1000):

@@ -150,6 +150,31 @@ def test_engine_large_system_shared_memory_path_on_host(oracle_mod):
         assert maxerr(got, w) < 1e-10
 
 
+@pytest.mark.parametrize("defines", [("HB_RK4_STAGE_LOOP=0",), ("HB_SOLVE_COLS=0",)])
+def test_large_system_switches_keep_results_on_host(defines, oracle_mod):
+    """chain12 with the RK4 stages unrolled instead of looped / the LDL^T and substitutions in row instead of column order:
+    the same results (the stage loop bit for bit, the solve order to rounding) against the oracle, RK4 and adaptive."""
+    lib, prm, s = harness("chain12", defines=defines)
+    ref, _, _ = harness("chain12")
+    o = oracle_mod.OracleSystem.builtin(BOXES["chain12"][0])
+    ys = random_phases("chain12", 3)
+    want, bad = o.batch_step(ys, 0, 0.01, 2)
+    want45, bad45 = o.batch_step(ys, 1, 0.01, 1)
+    assert bad == 0 and bad45 == 0
+    for y, w, w45 in zip(ys, want, want45):
+        got, base = y.copy(), y.copy()
+        assert lib.rk4_steps(_p(prm), _p(got), C.c_double(0.01), 2) == 0
+        assert ref.rk4_steps(_p(prm), _p(base), C.c_double(0.01), 2) == 0
+        assert maxerr(got, w) < 1e-10
+        if defines == ("HB_RK4_STAGE_LOOP=0",):
+            assert np.array_equal(got, base)
+        else:
+            assert maxerr(got, base) < 1e-13
+        got = y.copy()
+        assert lib.rkf45_steps(_p(prm), _p(got), C.c_double(0.01), 1) == 0
+        assert maxerr(got, w45) < 1e-10
+
+
 def test_engine_at_the_largest_supported_size_on_host(oracle_mod):
     """n = HB_MAX_N = 16: a 16-link chain (System 32 16) traced as a user system — symbolic stage, generated hpre / hpost, the
     16 x 16 LDL^T and the shared-memory RK4, against the oracle's tape interpreter (dense jets + explicit inverse)."""
@@ -350,6 +375,21 @@ def test_kernel_flags_and_slow_retry_on_host(oracle_mod):
     assert maxerr(buf, want) < 1e-10 * 2
 
 
+def test_kernel_slow_retry_outside_the_exp_domain_on_host(oracle_mod):
+    """room: 25 units outside a wall the logistic's exp argument (beta = 22) leaves hb_exp's domain |x| < 512; the kernel body
+    redoes that trajectory out of line with libm's exp and still matches the oracle (in place)."""
+    lib, prm, s = harness("room")
+    o = oracle_mod.OracleSystem.builtin(2)
+    y = random_phases("room", 64)
+    y[2, 0] = 25.0
+    y[33, 1] = -25.0
+    want, bad = o.batch_step(y, 0, 0.01, 2)
+    assert bad == 0 and np.all(np.isfinite(want))
+    buf = y.copy()
+    run_kernel(lib, prm, K_STEP_RK4, buf, buf, 64, dt=0.01, nsteps=2, grid=1)
+    assert maxerr(buf, want) < 1e-10 * 2
+
+
 @pytest.mark.parametrize("layout", [AOS, SOA])
 def test_init_random_kernel_on_host_is_bit_identical(layout, oracle_mod):
     lib, prm, s = harness("double_pendulum")
@@ -362,7 +402,7 @@ def test_init_random_kernel_on_host_is_bit_identical(layout, oracle_mod):
     assert np.array_equal(out if layout == AOS else out.T, want)
 
 
-@pytest.mark.parametrize("defines", [("HB_UNROLL2=1",), ("HB_L2_PREFETCH=1",), ("HB_LAYSPEC=0",), ("HB_SR_2OP=1", "HB_SC_LITERALS=1")])
+@pytest.mark.parametrize("defines", [("HB_LAYSPEC=0",), ("HB_SOLVE_COLS=0",), ("HB_REG_PREFETCH=0", "HB_ASYNC_STAGE=0"), ("HB_SC_CW2=1",)])
 def test_engine_experiment_switches_keep_results_on_host(defines, oracle_mod):
     """The compile-time experiment switches of the engine (profiles/ A/Bs, round-2 candidates) must not change results:
     same kernels, same ragged batch, against the oracle."""

@@ -321,6 +321,24 @@ def test_out_of_domain_angles_take_the_slow_path(oracle_mod):
     assert maxerr(e[:, 2], [o.hamiltonian(r[:2], r[2:]) for r in y]) < 1e-9
 
 
+def test_out_of_domain_exp_takes_the_slow_path(oracle_mod):
+    """The room's logistic walls (app/Examples.hs:601-605) evaluate exp(-beta (x - pos)) with beta = 22: 25 units outside the
+    walls the argument leaves the table-driven hb_exp's domain (|x| < 512) and the trajectory is redone out of line with
+    libdevice's exp.  Mixed into warps of ordinary trajectories; RK4, the adaptive stepper and hamEqs; in place too."""
+    g, o = systems_for("room", oracle_mod)
+    y = random_phases("room", 96)
+    y[2, 0] = 25.0; y[33, 1] = -25.0; y[64, 0] = -24.5; y[64, 1] = 26.0
+    yo, bad = o.batch_step(y, 0, 0.01, 3)
+    assert bad == 0 and np.all(np.isfinite(yo))
+    got = g.batch_step(y, 0.01, 3, integ=L.RK4)
+    assert maxerr(got, yo) < 3e-10
+    buf = y.copy()
+    g.batch_step(buf, 0.01, 3, integ=L.RK4, out=buf)
+    assert np.array_equal(buf, got)
+    assert maxerr(g.batch_step(y, 0.01, 1, integ=L.RKF45_GSL), o.batch_step(y, 1, 0.01, 1)[0]) < 1e-10
+    assert maxerr(g.batch_ham_eqs(y), o.batch_ham_eqs(y)) < 1e-10
+
+
 def _random_system(rng, m, n):
     """A random smooth coordinate map f: R^n -> R^m with full column rank near the origin and a random potential,
     written against hamilton_b200.num like a user would write mkSystem's arguments."""
