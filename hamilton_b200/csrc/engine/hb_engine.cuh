@@ -556,20 +556,21 @@ HB_DEV void hb_spd_solve_v(double* A, const BV b, double* x, int& minpiv) {
     // consecutive DFMAs write DIFFERENT accumulators and share one operand (operand-reuse cache).  The row-oriented (dot
     // product) order below has the same dependency graph per element, but ptxas emits it as written: runs of DFMAs on ONE
     // accumulator, 8 clocks apart — with two warps per scheduler (large systems) a third of all warp samples of the chain's
-    // step waited on those chains (profiles/r2u).  The factorisation and the forward substitution do per element exactly the
-    // operations of the row-oriented form in the same order (bit-identical); the backward substitution accumulates in
-    // descending instead of ascending column order (last-bit differences).
+    // step waited on those chains (profiles/r2u).  Per element the operations are those of the row-oriented form in the same
+    // order, except that L_jk d_k is taken as the unscaled entry it came from and that the backward substitution accumulates in
+    // descending instead of ascending column order (last-bit differences, on the accurate side).
     hb_static_for<0, N>([&](auto kt) {
       HB_IDX(k, kt);
       const double d = A[hb_tri(k, k)];
       hb_piv(minpiv, d);
       const double id = hb_rcp(d);
       invd[k] = id;
-      hb_static_for<k + 1, N>([&](auto it) { HB_IDX(i, it); A[hb_tri(i, k)] *= id; });   // column k: t_ik -> L_ik
-      hb_static_for<k + 1, N>([&](auto jt) {   // column j of the trailing matrix: A_ij -= L_ik (L_jk d_k), i >= j
+      double v[N - k > 1 ? N - k - 1 : 1];   // v_j = L_jk d_k = the unscaled column entry t_jk itself: no multiply (the row form
+                                             // stores only L and recomputes it as (t_jk / d_k) d_k: 66 DMULs per 12 x 12 solve)
+      hb_static_for<k + 1, N>([&](auto it) { HB_IDX(i, it); v[i - k - 1] = A[hb_tri(i, k)]; A[hb_tri(i, k)] = v[i - k - 1] * id; });   // t_ik -> L_ik
+      hb_static_for<k + 1, N>([&](auto jt) {   // column j of the trailing matrix: A_ij -= L_ik t_jk, i >= j
         HB_IDX(j, jt);
-        const double v = A[hb_tri(j, k)] * d;                     // L_jk d_k  (as the row form computes it)
-        hb_static_for<j, N>([&](auto it) { HB_IDX(i, it); A[hb_tri(i, j)] = fma(-A[hb_tri(i, k)], v, A[hb_tri(i, j)]); });
+        hb_static_for<j, N>([&](auto it) { HB_IDX(i, it); A[hb_tri(i, j)] = fma(-A[hb_tri(i, k)], v[j - k - 1], A[hb_tri(i, j)]); });
       });
     });
 #else
