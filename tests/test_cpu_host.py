@@ -446,3 +446,19 @@ def test_evolve_rejects_a_zero_length_first_interval_for_the_adaptive_integrator
     with pytest.raises(hb.HamiltonError) as ei:
         s.batch_step(buf[1:].reshape(4, 4), 0.01)
     assert ei.value.status == L.ERR_INVALID
+
+
+def test_host_and_engine_agree_on_the_shared_memory_constants():
+    """csrc/runtime.cpp sizes the dynamic shared memory of every launch from constants it cannot include from the engine header
+    (the header is CUDA): the two definitions must say the same, and HB_TAB_BYTES must hold the staged table image
+    (2048 sin/cos pairs + 64 powers of two + the mbarrier)."""
+    import re
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "hamilton_b200", "csrc")
+    eng = open(os.path.join(root, "engine", "hb_engine.cuh")).read()
+    run = open(os.path.join(root, "runtime.cpp")).read()
+    for name in ("HB_TAB_BYTES", "HB_BIG_N", "HB_WSTORE_MAXD"):
+        a = re.search(r"#define\s+%s\s+(\d+)" % name, eng)
+        b = re.search(r"#define\s+%s\s+(\d+)" % name, run)
+        assert a and b and a.group(1) == b.group(1), (name, a and a.group(1), b and b.group(1))
+    tab = int(re.search(r"#define\s+HB_TAB_BYTES\s+(\d+)", eng).group(1))
+    assert tab >= 2048 * 16 + 64 * 8 + 8 and tab % 128 == 0
