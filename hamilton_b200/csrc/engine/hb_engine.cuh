@@ -522,7 +522,7 @@ HB_DEV void hb_spd_solve_v(double* A, const BV b, double* x, int& minpiv) {
     hb_piv(minpiv, A[0]);
     x[0] = b(0) * hb_rcp(A[0]);
   } else if constexpr (N == 2 && CLOSED) {
-    const double det = fma(A[0], A[2], -A[1] * A[1]);
+    const double det = fma(-A[1], A[1], A[0] * A[2]);   // diagonal product on its own: a literal when the system compiler emitted constant diagonals (pendulums)
     hb_piv(minpiv, A[0]);
     hb_piv(minpiv, det);
     const double id = hb_rcp(det);
@@ -536,8 +536,9 @@ HB_DEV void hb_spd_solve_v(double* A, const BV b, double* x, int& minpiv) {
     // back-to-back reciprocal chains (this engine runs at 4-6 warps per scheduler, so latency is throughput);
     // positive leading minors (a, ad - b^2, det) <=> SPD
     const double m00 = A[0], m10 = A[1], m11 = A[2], m20 = A[3], m21 = A[4], m22 = A[5];
-    const double c00 = fma(m11, m22, -m21 * m21), c01 = fma(m20, m21, -m10 * m22), c02 = fma(m10, m21, -m20 * m11);
-    const double c11 = fma(m00, m22, -m20 * m20), c12 = fma(m10, m20, -m00 * m21), c22 = fma(m00, m11, -m10 * m10);
+    // products of two diagonal entries stand alone: literals when the system compiler emitted constant diagonals (pendulums)
+    const double c00 = fma(-m21, m21, m11 * m22), c01 = fma(m20, m21, -m10 * m22), c02 = fma(m10, m21, -m20 * m11);
+    const double c11 = fma(-m20, m20, m00 * m22), c12 = fma(m10, m20, -m00 * m21), c22 = fma(-m10, m10, m00 * m11);
     const double det = fma(m00, c00, fma(m10, c01, m20 * c02));
     hb_piv(minpiv, m00);
     hb_piv(minpiv, c22);

@@ -22,6 +22,13 @@ int Graph::constant(double c) {
   return intern({Op::Const, -1, -1, c});
 }
 
+// a = coef * base with a literal coefficient (1 when a is not such a product)
+static void split_coef(const Graph& G, int a, double* coef, int* base) {
+  double c;
+  if (G.nodes[a].op == Op::Mul && G.is_const(G.nodes[a].a, &c)) { *coef = c; *base = G.nodes[a].b; }
+  else { *coef = 1.0; *base = a; }
+}
+
 int Graph::add(int a, int b) {
   double x, y;
   if (is_const(a, &x) && is_const(b, &y)) return constant(x + y);
@@ -30,6 +37,11 @@ int Graph::add(int a, int b) {
   if (nodes[b].op == Op::Neg) return sub(a, nodes[b].a);
   if (nodes[a].op == Op::Neg) return sub(b, nodes[a].a);
   if (a == b) return mul(constant(2.0), a);   // x + x -> 2 x (merges with neighbouring constant factors)
+  {   // like terms: c1 x + c2 x -> (c1 + c2) x  (e.g. the gradient of m g (y1 + y2 + y3) of a pendulum chain: s + 2 s -> 3 s)
+    double ca, cb; int ba, bb;
+    split_coef(*this, a, &ca, &ba); split_coef(*this, b, &cb, &bb);
+    if (ba == bb && !is_const(ba)) return mul(constant(ca + cb), ba);
+  }
   if (a > b) std::swap(a, b);
   return intern({Op::Add, a, b, 0.0});
 }
@@ -42,6 +54,11 @@ int Graph::sub(int a, int b) {
   if (a == b) return constant(0.0);
   if (nodes[b].op == Op::Neg) return add(a, nodes[b].a);
   if (nodes[a].op == Op::Neg) return neg(add(nodes[a].a, b));
+  {   // like terms: c1 x - c2 x -> (c1 - c2) x
+    double ca, cb; int ba, bb;
+    split_coef(*this, a, &ca, &ba); split_coef(*this, b, &cb, &bb);
+    if (ba == bb && !is_const(ba)) return mul(constant(ca - cb), ba);
+  }
   return intern({Op::Sub, a, b, 0.0});
 }
 
