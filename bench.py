@@ -15,6 +15,9 @@ gaps between consecutive replays of one executable graph, which are launch plumb
   e2e        the same call through the C ABI with HOST buffers (pinned): H2D + kernel + D2H inside the timed region;
              e2e.by_nsteps repeats it with 16 and 100 RK4 steps per call (what an evolveHam-style caller does).
   roofline   HBM roofline of the dominant kernel (hbk_double_pendulum_dflt_step_rk4) + the instruction-issue view that binds it.
+  ham_eqs    explanation only: the path's central function on its own — ONE hamEqs evaluation per trajectory per launch
+             (hb_batch_ham_eqs) over the same ring of batches: the HBM-bound kernel of the path against the same roofline.
+  fused16 / chain / burst   explanation only: 16 steps per launch; a real stepping loop (L2-resident state); the K launches alone.
   cpu_baseline   the CPU oracle (restatement of the reference algorithm) on this box's host cores, the SAME 1,048,576 batch.
   configs    BASELINE configs[2], [3], [4] measured the same way (`--config 3|4|5` makes one of them the whole run):
              "3" 2,097,152 pendulums (System 2 1) + 2,097,152 two-body orbits (System 4 2) (two streams or one, whichever is faster),
