@@ -462,3 +462,16 @@ def test_host_and_engine_agree_on_the_shared_memory_constants():
         assert a and b and a.group(1) == b.group(1), (name, a and a.group(1), b and b.group(1))
     tab = int(re.search(r"#define\s+HB_TAB_BYTES\s+(\d+)", eng).group(1))
     assert tab >= 2048 * 16 + 64 * 8 + 8 and tab % 128 == 0
+
+
+@pytest.mark.parametrize("sid,bound", [(0, 14), (1, 70), (6, 124), (7, 1130)])
+def test_system_compiler_operation_counts_do_not_regress(sid, bound):
+    """Arithmetic operations per RHS of the symbolic hamEqs form, as the system compiler's cost model counts them (a
+    transcendental = 14).  The kernels are instruction-issue-bound, so every operation the compiler leaves in the DAG is
+    paid for: like-term collection (c1 x + c2 x) took the 12-link chain from 1195 to 1130 and the triple pendulum's gravity
+    gradient from 5 (s + 2 s) to 15 s.  Pendulum, double pendulum, triple pendulum, chain12."""
+    src = hb.systems.builtin(sid).source()
+    m = re.search(r"cost model: symbolic (\d+), direct (\d+)", src)
+    assert m, src[:300]
+    assert int(m.group(1)) <= bound, (int(m.group(1)), bound)
+    assert "hamEqs form: symbolic" in src
